@@ -1,0 +1,146 @@
+// ee_trbak.cu -- compact-WY back-transformation  Z <- H_{n-1} ... H_1 Z  on B200.
+//
+// Replaces eigen_common_trbakwy / eigen_trbakwy_body / trbakwy_datacast
+// (src/trbakwy4.F:77,227,655) and eigen_trbakwy_block_body(1,2) (src/trbakwy4_body.F:107-741).
+// Per block of mb reflectors V = [u_i ... u_{i+mb-1}] (column u_j has j rows, zero below):
+//     S = -V^T V (lower), S_jj <- S_jj/2 (0 -> 1)        (trbakwy4_body.F:206-213,302-313)
+//     Z <- Z + V S^{-1} (V^T Z)                            (trbakwy4_body.F:604-608,687-725)
+// Like the reference's blocked part, beta from the forward pass is not used; unlike the
+// reference there is no separate unblocked "head" (trbakwy4.F:345-499): the leading
+// (n-1) mod mb reflectors simply form a first, shorter block.
+// All O(n^2 mb) work is FP64 tensor-core GEMM (ee_gemm.cu); on a P x Q grid the V panel is
+// assembled replicated (one all-reduce of disjoint pieces) and V^T Z is summed over the
+// x group, as in trbakwy4_body.F:235.
+#include "ee_common.cuh"
+#include "ee_comm.h"
+
+namespace ee {
+
+namespace {
+
+constexpr int MB_MAX = 128;
+constexpr int KSPLIT = 64;
+
+// V(g, c) = u_{i0+c}(g) for g < i0+c, from the local cyclic pieces of a (zero elsewhere)
+__global__ void gather_v_kernel(const double *A, int lda, int px, int py, int x, int y, int i0, int mb, int rows,
+                                double *V, int ldv)
+{
+    const int c = blockIdx.y;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ldv) return;
+    const int gc = i0 + c;
+    double v = 0.0;
+    if (c < mb && g < gc && g < rows && (gc % py) == y && (g % px) == x) v = A[(size_t)(gc / py) * lda + g / px];
+    V[(size_t)c * ldv + g] = v;
+}
+
+// local rows of the replicated panel: Vx(jl, c) = V(jl*px + x, c)
+__global__ void pick_rows_kernel(const double *V, int ldv, int px, int x, int nrl, double *Vx, int ldvx)
+{
+    const int c = blockIdx.y;
+    const int jl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (jl >= ldvx) return;
+    Vx[(size_t)c * ldvx + jl] = (jl < nrl) ? V[(size_t)c * ldv + (size_t)jl * px + x] : 0.0;
+}
+
+// T = S^{-1},  S = -(sum of split-K partials of V^T V) lower, diagonal halved (0 -> 1).
+// One CTA; thread j solves S x = e_j by forward substitution (column j of T).
+__global__ void __launch_bounds__(MB_MAX) tinv_kernel(const double *SMpart, int nsplit, int mb, double *T)
+{
+    extern __shared__ double S[];  // mb x (mb+1) row-major-ish: S[i*(mb+1)+k]
+    const int ld = mb + 1;
+    for (int idx = threadIdx.x; idx < mb * mb; idx += blockDim.x) {
+        int i = idx % mb, k = idx / mb;  // column-major partials: (i,k) at i + k*mb
+        double s = 0.0;
+        for (int z = 0; z < nsplit; z++) s += SMpart[(size_t)z * mb * mb + idx];
+        s = -s;
+        if (i == k) s = (s == 0.0) ? 1.0 : 0.5 * s;
+        S[i * ld + k] = s;
+    }
+    __syncthreads();
+    const int j = threadIdx.x;
+    if (j < mb) {
+        // x lives in column j of T (global memory, L1/L2 resident)
+        for (int i = 0; i < j; i++) T[(size_t)j * mb + i] = 0.0;
+        T[(size_t)j * mb + j] = 1.0 / S[j * ld + j];
+        for (int i = j + 1; i < mb; i++) {
+            double s0 = 0.0, s1 = 0.0;
+            int k = j;
+            for (; k + 1 < i; k += 2) {
+                s0 = fma(S[i * ld + k], T[(size_t)j * mb + k], s0);
+                s1 = fma(S[i * ld + k + 1], T[(size_t)j * mb + k + 1], s1);
+            }
+            if (k < i) s0 = fma(S[i * ld + k], T[(size_t)j * mb + k], s0);
+            T[(size_t)j * mb + i] = -(s0 + s1) / S[i * ld + i];
+        }
+    }
+}
+
+}  // namespace
+
+void trbak_dev(int n, int nvec, const double *a, int lda, double *z, int ldz, const double *e, int m_backward)
+{
+    (void)e;
+    Context &c = ctx();
+    const Grid &g = c.g;
+    cudaStream_t st = c.stream;
+    if (n <= 1 || nvec <= 0) return;
+    int mb = m_backward < MB_MAX ? m_backward : MB_MAX;
+    if (mb < 1) mb = 1;
+    if (mb > n - 1) mb = n - 1;
+    const int nvl = cyc_count(nvec, g.py, g.y);
+    const bool multi = g.nnod > 1;
+    const int ldv = (n + 15) & ~15;
+    const int nrl_max = cyc_count(n, g.px, g.x);
+    const int ldvx = ((nrl_max > 0 ? nrl_max : 1) + 15) & ~15;
+    double *V = (double *)dev_alloc((size_t)ldv * mb * sizeof(double));
+    double *Vx = (g.px > 1) ? (double *)dev_alloc((size_t)ldvx * mb * sizeof(double)) : V;
+    double *SMp = (double *)dev_alloc((size_t)KSPLIT * mb * mb * sizeof(double));
+    double *T = (double *)dev_alloc((size_t)mb * mb * sizeof(double));
+    const int ldss = mb;
+    double *SS = (double *)dev_alloc((size_t)ldss * (nvl > 0 ? nvl : 1) * sizeof(double));
+    double *SS2 = (double *)dev_alloc((size_t)ldss * (nvl > 0 ? nvl : 1) * sizeof(double));
+    EE_CUDA(cudaFuncSetAttribute(tinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MB_MAX * (MB_MAX + 1) * sizeof(double))));
+
+    // reflector columns i = 1..n-1 ; first block takes the remainder (trbakwy4.F:292)
+    int i0 = 1;
+    int first = (n - 1) % mb;
+    while (i0 <= n - 1) {
+        const int cur = (i0 == 1 && first != 0) ? first : mb;
+        const int rows = i0 + cur - 1;  // longest reflector of the block
+        const int nrl = cyc_count(rows, g.px, g.x);
+        // ---- V panel (K15) ---------------------------------------------------------------
+        {
+            dim3 grid((ldv + 255) / 256, cur);
+            gather_v_kernel<<<grid, 256, 0, st>>>(a, lda, g.px, g.py, g.x, g.y, i0, cur, rows, V, ldv);
+            EE_CHECK_LAUNCH();
+            if (multi) comm_allreduce_sum(V, (size_t)ldv * cur, COMM_WORLD, st);
+            if (g.px > 1) {
+                dim3 grid2((ldvx + 255) / 256, cur);
+                pick_rows_kernel<<<grid2, 256, 0, st>>>(V, ldv, g.px, g.x, nrl, Vx, ldvx);
+                EE_CHECK_LAUNCH();
+            }
+        }
+        const int ldx = (g.px > 1) ? ldvx : ldv;
+        // ---- S = -V^T V from the replicated panel (split-K partials), T = S^{-1} (K12,K13) ---
+        int ks = rows / 512; if (ks < 1) ks = 1; if (ks > KSPLIT) ks = KSPLIT;
+        dgemm_ex(st, 'T', 'N', cur, cur, rows, 1.0, V, ldv, V, ldv, 0.0, SMp, cur, ks, (long long)cur * cur);
+        tinv_kernel<<<1, MB_MAX, (size_t)cur * (cur + 1) * sizeof(double), st>>>(SMp, ks, cur, T);
+        EE_CHECK_LAUNCH();
+        if (nvl > 0) {
+            // ---- SS = Vx^T Z  (K12) ; sum over the x group (C13) ---------------------------
+            if (nrl > 0) dgemm(st, 'T', 'N', cur, nvl, nrl, 1.0, Vx, ldx, z, ldz, 0.0, SS, ldss);
+            else EE_CUDA(cudaMemsetAsync(SS, 0, (size_t)ldss * nvl * sizeof(double), st));
+            if (g.px > 1) comm_allreduce_sum(SS, (size_t)ldss * nvl, COMM_X, st);
+            // ---- SS2 = T SS ; Z += Vx SS2  (K14) ---------------------------------------------
+            dgemm(st, 'N', 'N', cur, nvl, cur, 1.0, T, cur, SS, ldss, 0.0, SS2, ldss);
+            if (nrl > 0) dgemm(st, 'N', 'N', nrl, nvl, cur, 1.0, Vx, ldx, SS2, ldss, 1.0, z, ldz);
+        }
+        i0 += cur;
+    }
+    EE_CUDA(cudaStreamSynchronize(st));
+    dev_free(V); if (g.px > 1) dev_free(Vx);
+    dev_free(SMp); dev_free(T); dev_free(SS); dev_free(SS2);
+}
+
+}  // namespace ee

@@ -1,0 +1,798 @@
+// ee_trd.cu -- blocked Householder tridiagonalisation on B200 (sm_100a).
+//
+// Replaces eigen_trd and its helpers (reference: src/eigen_trd.F:82-723,
+// src/eigen_trd_t2.F (au: SYMV + scalars), _t4 (compute_u), _t5/_t5x (panel update),
+// _t6_3 (compute_v), _t7 (panel load/restore), _t8 (init/final), src/eigen_t1.F (rank-2k)).
+//
+// B200-first design (not a translation):
+//  * the local part of A stays in HBM in the caller's 2D cyclic layout; every vector of the
+//    algorithm (current column, panel copy W, reflector panels U and V, p = A u) is kept
+//    FULL LENGTH and replicated on every rank, so one column step needs exactly one
+//    cross-rank reduction (of the partial p) instead of the reference's
+//    redistribution + 2 all-reduces + broadcast (src/eigen_trd_t2.F:426-567).
+//  * one column step = three launches, no host synchronisation anywhere:
+//      symv_kernel   streams the local strict upper "staircase" once (HBM-bound): each
+//                    element feeds a column dot and a row axpy (K1 of SURVEY 2.4), writes
+//                    deterministic per-tile partials; a few extra CTAs compute U^T u, V^T u.
+//      pvec_kernel   p = sum(partials) + diag*u - U s - V t ; partial u^T p.
+//      vvec_kernel   v = (p - alpha u)/beta ; forms the next column from the panel copy
+//                    (left-looking) and its norm; the last CTA finishes the Householder
+//                    scalars (g, u_L, beta) on the device.
+//  * the trailing update A -= U V^T + V U^T is one FP64 tensor-core (DMMA) GEMM with K = 2m
+//    on the upper staircase tiles (ee_gemm.cu).
+// All reductions have a fixed order: results are bit-reproducible run to run.
+#include "ee_common.cuh"
+#include "ee_comm.h"
+
+namespace ee {
+
+namespace {
+
+constexpr int TR = 128;     // tile rows (local)
+constexpr int TC = 64;      // tile cols (local)
+constexpr int SW = 4;       // sub-tiles swept per CTA along a row strip
+constexpr int NCH = 32;     // row chunks for the panel dot products
+constexpr int VROWS = 256;  // rows per CTA in the vector kernels
+constexpr int MAXM = 256;   // max panel width
+
+struct TrdP {
+    double *A; int lda;                 // local matrix, padded (lda % TR == 0, cols % TC == 0)
+    int px, py, x, y;                   // grid
+    int n, npad;                        // global size, leading dim of replicated panels
+    int L;                              // reflector length = global column index i (0-based)
+    int k, m0, ndone;                   // slot in panel, panel width, finished pairs (slots k+1..m0-1)
+    int i_base;
+    double *U, *V, *W;                  // replicated panels, npad x m
+    double *ucur, *unext;               // current / next raw column (length npad)
+    double *Prow, *Pcol; int ldprow, ldpcol;
+    double *dots_part;                  // [NCH][2*MAXM]
+    double *st;                         // [2*MAXM]  s_l = V_l^T u, t_l = U_l^T u (l = k+1+idx)
+    double *pbuf;                       // p (length npad)
+    double *part;                       // [2][maxblocks] partial sums (utp / norm)
+    double *scal;                       // [0]=g [1]=u_n [2]=beta [3]=alpha
+    unsigned int *tickets;              // [4]
+    double *d_out, *e_out;
+    int has_next;                       // vvec: build next column
+    int first;                          // vvec: panel prologue only (no v to form)
+};
+
+// --- staircase geometry shared by writer (symv) and reader (pvec) ------------------------
+// number of local columns with global index < L
+__device__ __forceinline__ int ncl_of(const TrdP &P) { return cyc_count(P.L, P.py, P.y); }
+// number of active tile rows for sub-tile column t: tile rows br with some row g_row < max col g
+__device__ __forceinline__ int ntile_rows(const TrdP &P, int t, int nclL)
+{
+    int clast = min((t + 1) * TC, nclL) - 1;         // last local col of the sub-tile within L
+    if (clast < t * TC) return 0;
+    long long cmax_g = (long long)clast * P.py + P.y;  // its global index
+    // rows br*TR*px + x < cmax_g
+    if (cmax_g <= P.x) return 0;
+    return (int)((cmax_g - P.x - 1) / ((long long)TR * P.px)) + 1;
+}
+__device__ __forceinline__ int nstrips_of(int nclL) { return (nclL + SW * TC - 1) / (SW * TC); }
+__device__ __forceinline__ int strip_rows(const TrdP &P, int sc, int nclL)
+{
+    int tlast = min((sc + 1) * SW, (nclL + TC - 1) / TC) - 1;
+    return ntile_rows(P, tlast, nclL);
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum (result valid in thread 0), fixed order
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double *sm)
+{
+    v = warp_sum(v);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sm[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NT / 32; i++) r += sm[i];
+    }
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// SYMV over the local strict upper staircase + panel dot products
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void symv_strip(const TrdP &P, int br, int sc, int nclL, double *smem)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = br * TR;
+    const double *__restrict__ u = P.ucur;
+    // this thread's 4 rows
+    int rloc[4] = {r0 + 2 * lane, r0 + 2 * lane + 1, r0 + 64 + 2 * lane, r0 + 64 + 2 * lane + 1};
+    double ux[4], acc_row[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        long long g = (long long)rloc[q] * P.px + P.x;
+        ux[q] = (g < P.L) ? __ldg(u + g) : 0.0;
+        acc_row[q] = 0.0;
+    }
+    const long long rmax_g = (long long)(r0 + TR - 1) * P.px + P.x;
+    for (int st = 0; st < SW; st++) {
+        const int t = sc * SW + st;
+        const int c0 = t * TC;
+        if (c0 >= nclL) break;
+        if (br >= ntile_rows(P, t, nclL)) continue;
+        const int cw = c0 + 8 * warp;
+        const double *__restrict__ base = P.A + (size_t)cw * P.lda + r0 + 2 * lane;
+        double2 v0[8], v1[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            v0[c] = __ldcs(reinterpret_cast<const double2 *>(base + (size_t)c * P.lda));
+            v1[c] = __ldcs(reinterpret_cast<const double2 *>(base + (size_t)c * P.lda + 64));
+        }
+        double uy[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            long long g = (long long)(cw + c) * P.py + P.y;
+            uy[c] = (g < P.L) ? __ldg(u + g) : 0.0;
+        }
+        const long long cmin_g = (long long)c0 * P.py + P.y;
+        const long long cmax_g = (long long)(c0 + TC - 1) * P.py + P.y;
+        const bool interior = (rmax_g < cmin_g) && (cmax_g < P.L);
+        if (!interior) {
+            long long gr[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) gr[q] = (long long)rloc[q] * P.px + P.x;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                long long gc = (long long)(cw + c) * P.py + P.y;
+                bool cin = gc < P.L;
+                if (!(cin && gr[0] < gc)) v0[c].x = 0.0;
+                if (!(cin && gr[1] < gc)) v0[c].y = 0.0;
+                if (!(cin && gr[2] < gc)) v1[c].x = 0.0;
+                if (!(cin && gr[3] < gc)) v1[c].y = 0.0;
+            }
+        }
+        double acc_col[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            acc_row[0] = fma(v0[c].x, uy[c], acc_row[0]);
+            acc_row[1] = fma(v0[c].y, uy[c], acc_row[1]);
+            acc_row[2] = fma(v1[c].x, uy[c], acc_row[2]);
+            acc_row[3] = fma(v1[c].y, uy[c], acc_row[3]);
+            double s = v0[c].x * ux[0];
+            s = fma(v0[c].y, ux[1], s);
+            s = fma(v1[c].x, ux[2], s);
+            s = fma(v1[c].y, ux[3], s);
+            acc_col[c] = s;
+        }
+        // reduce-scatter the 8 column sums over the 32 lanes (9 exchanges instead of 40)
+        {
+            const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+            double h[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                double mine = b4 ? acc_col[q + 4] : acc_col[q];
+                double other = b4 ? acc_col[q] : acc_col[q + 4];
+                h[q] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
+            }
+            double h2[2];
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                double mine = b3 ? h[q + 2] : h[q];
+                double other = b3 ? h[q] : h[q + 2];
+                h2[q] = mine + __shfl_xor_sync(0xffffffffu, other, 8);
+            }
+            double mine = b2 ? h2[1] : h2[0];
+            double other = b2 ? h2[0] : h2[1];
+            double r = mine + __shfl_xor_sync(0xffffffffu, other, 4);
+            r += __shfl_xor_sync(0xffffffffu, r, 2);
+            r += __shfl_xor_sync(0xffffffffu, r, 1);
+            if ((lane & 3) == 0) {
+                int c = (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0);
+                P.Pcol[(size_t)br * P.ldpcol + cw + c] = r;
+            }
+        }
+    }
+    // cross-warp reduction of the row sums
+    double *sm = smem;  // [8][TR]
+    __syncthreads();
+    sm[warp * TR + 2 * lane] = acc_row[0];
+    sm[warp * TR + 2 * lane + 1] = acc_row[1];
+    sm[warp * TR + 64 + 2 * lane] = acc_row[2];
+    sm[warp * TR + 64 + 2 * lane + 1] = acc_row[3];
+    __syncthreads();
+    if (threadIdx.x < TR) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) s += sm[w * TR + threadIdx.x];
+        P.Prow[(size_t)sc * P.ldprow + r0 + threadIdx.x] = s;
+    }
+}
+
+// chunk of the panel dot products  s_l = V_l^T u, t_l = U_l^T u  (finished slots k+1..m0-1)
+__device__ void dots_chunk(const TrdP &P, int ch, double *smem)
+{
+    const int nd = P.ndone;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // 8 warps
+    const int rows_per = ((P.L + NCH - 1) / NCH + 31) & ~31;
+    const int j0 = ch * rows_per, j1 = min(P.L, j0 + rows_per);
+    // each warp takes columns l = warp, warp+8, ... of the 2*nd vectors
+    for (int c = warp; c < 2 * nd; c += 8) {
+        const double *col = (c < nd) ? (P.V + (size_t)(P.k + 1 + c) * P.npad)
+                                     : (P.U + (size_t)(P.k + 1 + c - nd) * P.npad);
+        double s = 0.0;
+        for (int j = j0 + lane; j < j1; j += 32) s = fma(__ldg(col + j), __ldg(P.ucur + j), s);
+        s = warp_sum(s);
+        if (lane == 0) P.dots_part[(size_t)ch * 2 * MAXM + c] = s;
+    }
+    // last chunk CTA reduces the partials in fixed order
+    __shared__ unsigned int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&P.tickets[0], 1u);
+    __syncthreads();
+    if (s_last == NCH - 1) {
+        __threadfence();
+        for (int c = threadIdx.x; c < 2 * nd; c += blockDim.x) {
+            double s = 0.0;
+            for (int q = 0; q < NCH; q++) s += __ldcg(P.dots_part + (size_t)q * 2 * MAXM + c);
+            P.st[c] = s;
+        }
+        if (threadIdx.x == 0) P.tickets[0] = 0u;
+    }
+    (void)smem;
+}
+
+__global__ void __launch_bounds__(256, 2) symv_kernel(TrdP P, int gx, int ntile_blocks)
+{
+    __shared__ double smem[8 * TR];
+    const int bid = blockIdx.x;
+    if (bid >= ntile_blocks) {
+        if (P.ndone > 0) dots_chunk(P, bid - ntile_blocks, smem);
+        return;
+    }
+    const int nclL = ncl_of(P);
+    const int nsc = nstrips_of(nclL);
+    const int bx = bid % gx, by = bid / gx;
+    // fold the triangle: pair strip (nsc-1-bx) with strip bx
+    const int sc1 = nsc - 1 - bx, sc2 = bx;
+    const int n1 = strip_rows(P, sc1, nclL);
+    int sc, br;
+    if (by < n1) { sc = sc1; br = by; }
+    else {
+        if (sc2 == sc1) return;
+        br = by - n1; sc = sc2;
+        if (br >= strip_rows(P, sc2, nclL)) return;
+    }
+    symv_strip(P, br, sc, nclL, smem);
+}
+
+// ---------------------------------------------------------------------------------------
+// p = A u (from partials) - U s - V t ; partial u^T p ; last CTA: alpha
+// MODE 0: fused (single rank)   MODE 1: partial only (write p_partial)   MODE 2: post-allreduce
+// ---------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(VROWS) pvec_kernel(TrdP P)
+{
+    __shared__ double s_st[2 * MAXM];
+    __shared__ int s_nbr[1024];
+    __shared__ double s_red[VROWS / 32];
+    __shared__ unsigned int s_last;
+    const int nd = P.ndone;
+    const int nclL = ncl_of(P);
+    const int nsc = nstrips_of(nclL);
+    if (MODE != 2) {
+        for (int s = threadIdx.x; s < nsc; s += blockDim.x) s_nbr[s] = strip_rows(P, s, nclL);
+    }
+    if (MODE != 1) {
+        for (int c = threadIdx.x; c < 2 * nd; c += blockDim.x) s_st[c] = P.st[c];
+    }
+    __syncthreads();
+    const int g = blockIdx.x * VROWS + threadIdx.x;
+    double up = 0.0;
+    if (g < P.L) {
+        double p = 0.0;
+        const double ug = P.ucur[g];
+        if (MODE != 2) {
+            const bool rown = (g % P.px) == P.x, coln = (g % P.py) == P.y;
+            if (rown) {
+                const int jl = g / P.px, br = jl / TR;
+                for (int s = nsc - 1; s >= 0 && s_nbr[s] > br; s--) p += __ldcs(P.Prow + (size_t)s * P.ldprow + jl);
+            }
+            if (coln) {
+                const int il = g / P.py;
+                const int nb = ntile_rows(P, il / TC, nclL);
+                for (int b = 0; b < nb; b++) p += __ldcs(P.Pcol + (size_t)b * P.ldpcol + il);
+                if (rown) p = fma(P.A[(size_t)il * P.lda + g / P.px], ug, p);
+            }
+        } else {
+            p = P.pbuf[g];
+        }
+        if (MODE != 1) {
+            // corrections with the finished pairs of this panel
+            for (int l = 0; l < nd; l++) {
+                const size_t off = (size_t)(P.k + 1 + l) * P.npad + g;
+                p = fma(-__ldg(P.U + off), s_st[l], p);
+                p = fma(-__ldg(P.V + off), s_st[nd + l], p);
+            }
+            up = ug * p;
+        }
+        P.pbuf[g] = p;
+    }
+    if (MODE == 1) return;
+    double bs = block_sum<VROWS>(up, s_red);
+    if (threadIdx.x == 0) {
+        P.part[blockIdx.x] = bs;
+        __threadfence();
+        s_last = atomicAdd(&P.tickets[1], 1u);
+    }
+    __syncthreads();
+    if (s_last == gridDim.x - 1) {
+        __threadfence();
+        double s = 0.0;
+        for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) s += __ldcg(P.part + q);
+        // fixed-order tree: per-thread strided sums then block_sum (deterministic for a given grid)
+        double tot = block_sum<VROWS>(s, s_red);
+        if (threadIdx.x == 0) {
+            double beta = P.scal[2];
+            P.scal[3] = tot / (2.0 * beta);  // alpha = u^T p / (2 beta)   (trd_t6_3.F:255-262)
+            P.tickets[1] = 0u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// v = (p - alpha u)/beta ; next raw column from the panel copy (left-looking) ; its norm;
+// last CTA: Householder scalars of the next column (trd_t2.F:574-614)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VROWS) vvec_kernel(TrdP P)
+{
+    __shared__ double s_ur[MAXM], s_vr[MAXM];  // row c of U and V for slots k..m0-1
+    __shared__ double s_red[VROWS / 32];
+    __shared__ unsigned int s_last;
+    const int L = P.L, k = P.k;
+    const int c = L - 1;  // next column (global), also the last row of u
+    double alpha = 0.0, beta = 1.0;
+    int nl;               // pairs applied to the next column: slots lo..m0-1
+    int lo;
+    if (!P.first) {
+        alpha = P.scal[3]; beta = P.scal[2];
+        lo = k;
+    } else {
+        lo = k + 1;  // panel prologue: no pairs yet (k = m0 - 1 -> nl = 0)
+    }
+    nl = P.m0 - lo;
+    if (P.has_next) {
+        for (int l = threadIdx.x; l < nl; l += blockDim.x) {
+            int slot = lo + l;
+            double ur, vr;
+            if (!P.first && slot == k) {
+                ur = P.ucur[c];
+                vr = (P.pbuf[c] - alpha * ur) / beta;
+            } else {
+                ur = P.U[(size_t)slot * P.npad + c];
+                vr = P.V[(size_t)slot * P.npad + c];
+            }
+            s_ur[l] = ur; s_vr[l] = vr;
+        }
+    }
+    __syncthreads();
+    const int g = blockIdx.x * VROWS + threadIdx.x;
+    double nrm = 0.0;
+    // rows 0..L-1 carry u,v ; the next column has rows 0..c (row c = its diagonal)
+    if (g < L || (P.first && g <= L)) {
+        double ug = 0.0, vg = 0.0;
+        if (!P.first) {
+            ug = P.ucur[g];
+            vg = (P.pbuf[g] - alpha * ug) / beta;
+            P.U[(size_t)k * P.npad + g] = ug;
+            P.V[(size_t)k * P.npad + g] = vg;
+        }
+        if (P.has_next) {
+            const int kn = P.first ? k : k - 1;  // slot of the next column
+            const int top = P.first ? L : c;     // its diagonal row
+            if (g <= top) {
+                double a = P.W[(size_t)kn * P.npad + g];
+                for (int l = 0; l < nl; l++) {
+                    int slot = lo + l;
+                    double uj, vj;
+                    if (!P.first && slot == k) { uj = ug; vj = vg; }
+                    else { uj = __ldg(P.U + (size_t)slot * P.npad + g); vj = __ldg(P.V + (size_t)slot * P.npad + g); }
+                    a = fma(-uj, s_vr[l], a);
+                    a = fma(-vj, s_ur[l], a);
+                }
+                P.unext[g] = a;
+                if (g < top) nrm = a * a;
+            }
+        }
+    }
+    if (!P.has_next) return;
+    double bs = block_sum<VROWS>(nrm, s_red);
+    if (threadIdx.x == 0) {
+        P.part[blockIdx.x] = bs;
+        __threadfence();
+        s_last = atomicAdd(&P.tickets[2], 1u);
+    }
+    __syncthreads();
+    if (s_last == gridDim.x - 1) {
+        __threadfence();
+        double s = 0.0;
+        for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) s += __ldcg(P.part + q);
+        double anorm2 = block_sum<VROWS>(s, s_red);
+        if (threadIdx.x == 0) {
+            const int top = P.first ? L : c;  // next column index i' ; reflector length = top
+            double a_n = __ldcg(P.unext + top - 1);
+            double dia = __ldcg(P.unext + top);
+            double g_n, u_n, bt;
+            if (anorm2 != 0.0) {
+                double nr = sqrt(anorm2);
+                g_n = -copysign(nr, a_n);
+                u_n = a_n - g_n;
+                bt = -u_n * g_n;
+            } else { g_n = 0.0; u_n = 0.0; bt = 1.0; }
+            P.scal[0] = g_n; P.scal[1] = u_n; P.scal[2] = bt;
+            P.unext[top - 1] = u_n;
+            P.e_out[top] = g_n;
+            P.d_out[top] = dia;
+            P.tickets[2] = 0u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// panel load: W(:,k) <- A(0..i_base+k, i_base+k)  (local pieces scattered to global rows)
+// ---------------------------------------------------------------------------------------
+__global__ void panel_load_kernel(TrdP P, int zero_first)
+{
+    const int k = blockIdx.y;
+    const int gc = P.i_base + k;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= P.npad) return;
+    double v = 0.0;
+    if (g <= gc && (gc % P.py) == P.y && (g % P.px) == P.x) v = P.A[(size_t)(gc / P.py) * P.lda + g / P.px];
+    P.W[(size_t)k * P.npad + g] = v;
+    if (zero_first) { P.U[(size_t)k * P.npad + g] = 0.0; P.V[(size_t)k * P.npad + g] = 0.0; }
+}
+
+// panel restore: reflector columns back into A (rows 0..gc-1 of processed columns)
+__global__ void panel_restore_kernel(TrdP P, int k_stop)
+{
+    const int k = blockIdx.y;
+    const int gc = P.i_base + k;
+    if ((gc % P.py) != P.y) return;
+    const int jl = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long g = (long long)jl * P.px + P.x;
+    if (k >= k_stop) {
+        if (g < gc) P.A[(size_t)(gc / P.py) * P.lda + jl] = P.U[(size_t)k * P.npad + g];
+    } else {
+        // first panel, columns 0 and 1: apply every pair of the panel to the panel copy
+        if (g <= gc) {
+            double a = P.W[(size_t)k * P.npad + g];
+            for (int slot = k_stop; slot < P.m0; slot++) {
+                a = fma(-P.U[(size_t)slot * P.npad + g], P.V[(size_t)slot * P.npad + gc], a);
+                a = fma(-P.V[(size_t)slot * P.npad + g], P.U[(size_t)slot * P.npad + gc], a);
+            }
+            P.A[(size_t)(gc / P.py) * P.lda + jl] = a;
+        }
+    }
+}
+
+// pack syr2k operands: UVx[jl][0..m) = U(g,:), [m..2m) = V(g,:) ; VUy[il] = [V | U]
+__global__ void pack_uv_kernel(TrdP P, double *UVx, int ldx, int nrl, double *VUy, int ldy, int ncl, int m)
+{
+    const int c = blockIdx.y;  // 0..2m-1
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const double *srcx = (c < m) ? P.U + (size_t)c * P.npad : P.V + (size_t)(c - m) * P.npad;
+    const double *srcy = (c < m) ? P.V + (size_t)c * P.npad : P.U + (size_t)(c - m) * P.npad;
+    if (idx < nrl) UVx[(size_t)c * ldx + idx] = srcx[(size_t)idx * P.px + P.x];
+    if (idx < ncl) VUy[(size_t)c * ldy + idx] = srcy[(size_t)idx * P.py + P.y];
+}
+
+// eigen_trd_final (trd_t8.F:188-219): e(1) = -A(0,1), A(0,1) *= 2, d(0), d(1), e(0) = 0
+__global__ void trd_final_kernel(TrdP P)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    // on a multi-rank grid the owners differ; contributions are summed by the caller
+    double t = 0.0, d0 = 0.0, d1 = 0.0;
+    if (P.n >= 2 && (1 % P.py) == P.y && (0 % P.px) == P.x) {
+        size_t off = (size_t)(1 / P.py) * P.lda + 0;
+        t = P.A[off];
+        P.A[off] = 2.0 * t;
+    }
+    if ((0 % P.py) == P.y && (0 % P.px) == P.x) d0 = P.A[0];
+    if (P.n >= 2 && (1 % P.py) == P.y && (1 % P.px) == P.x) d1 = P.A[(size_t)(1 / P.py) * P.lda + 1 / P.px];
+    P.scal[4] = -t; P.scal[5] = d0; P.scal[6] = d1;
+}
+__global__ void trd_final_store_kernel(TrdP P)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    P.e_out[0] = 0.0;
+    P.d_out[0] = P.scal[5];
+    if (P.n >= 2) { P.e_out[1] = P.scal[4]; P.d_out[1] = P.scal[6]; }
+}
+
+// zero the strictly lower part and the padding of the local matrix (trd_t8.F:84-94)
+__global__ void zero_lower_kernel(double *A, int lda, int ncols, int n, int px, int py, int x, int y)
+{
+    const int il = blockIdx.y;
+    const int jl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (jl >= lda || il >= ncols) return;
+    long long gr = (long long)jl * px + x, gc = (long long)il * py + y;
+    if (gr > gc || gr >= n || gc >= n) A[(size_t)il * lda + jl] = 0.0;
+}
+
+// max |a| over the upper triangle + non-finite flag (eigen_scaling.F:92-107)
+__global__ void absmax_kernel(const double *A, int lda, int n, int px, int py, int x, int y, int nrl, int ncl,
+                              double *out /* [0]=max, [1]=bad */)
+{
+    double mx = 0.0; int bad = 0;
+    for (int il = blockIdx.y; il < ncl; il += gridDim.y) {
+        long long gc = (long long)il * py + y;
+        for (int jl = blockIdx.x * blockDim.x + threadIdx.x; jl < nrl; jl += gridDim.x * blockDim.x) {
+            long long gr = (long long)jl * px + x;
+            if (gr <= gc) {
+                double t = A[(size_t)il * lda + jl];
+                if (isfinite(t)) mx = fmax(mx, fabs(t)); else bad = 1;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        // non-negative doubles order like unsigned 64-bit integers
+        atomicMax(reinterpret_cast<unsigned long long *>(out), (unsigned long long)__double_as_longlong(mx));
+        if (bad) atomicMax(reinterpret_cast<unsigned long long *>(out + 1), (unsigned long long)__double_as_longlong(1.0));
+    }
+}
+__global__ void scale_upper_kernel(double *A, int lda, int n, int px, int py, int x, int y, int nrl, int ncl, double s)
+{
+    const int il = blockIdx.y;
+    const int jl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (jl >= nrl || il >= ncl) return;
+    long long gr = (long long)jl * px + x, gc = (long long)il * py + y;
+    if (gr <= gc) A[(size_t)il * lda + jl] *= s;
+}
+
+}  // namespace
+
+// =========================================================================================
+// host drivers
+// =========================================================================================
+double scaling_dev(int n, double *a, int lda)
+{
+    Context &c = ctx();
+    const Grid &g = c.g;
+    const int nrl = cyc_count(n, g.px, g.x), ncl = cyc_count(n, g.py, g.y);
+    double *out = (double *)dev_alloc(2 * sizeof(double));
+    EE_CUDA(cudaMemsetAsync(out, 0, 2 * sizeof(double), c.stream));
+    if (nrl > 0 && ncl > 0) {
+        dim3 grid(min(64, (nrl + 255) / 256), min(ncl, 4096));
+        absmax_kernel<<<grid, 256, 0, c.stream>>>(a, lda, n, g.px, g.py, g.x, g.y, nrl, ncl, out);
+        EE_CHECK_LAUNCH();
+    }
+    comm_allreduce_max(out, 2, COMM_WORLD, c.stream);
+    double h[2];
+    EE_CUDA(cudaMemcpyAsync(h, out, sizeof h, cudaMemcpyDeviceToHost, c.stream));
+    EE_CUDA(cudaStreamSynchronize(c.stream));
+    dev_free(out);
+    if (h[1] != 0.0) return NAN;
+    // LAPACK dsyev convention, eigen_scaling.F:76-134
+    const double SAFMIN = 2.2250738585072014e-308, PREC = 2.220446049250313e-16;
+    const double SMLNUM = SAFMIN / PREC, BIGNUM = 1.0 / SMLNUM;
+    const double RMIN = sqrt(SMLNUM);
+    const double RMAX = fmin(sqrt(BIGNUM), 1.0 / sqrt(sqrt(SAFMIN)));
+    const double anrm = h[0];
+    double sigma = 1.0;
+    if (anrm != 0.0 && anrm < RMIN) sigma = RMIN / anrm;
+    else if (anrm > RMAX) sigma = RMAX / anrm;
+    if (sigma != 1.0 && nrl > 0 && ncl > 0) {
+        dim3 grid((nrl + 255) / 256, ncl);
+        scale_upper_kernel<<<grid, 256, 0, c.stream>>>(a, lda, n, g.px, g.py, g.x, g.y, nrl, ncl, sigma);
+        EE_CHECK_LAUNCH();
+    }
+    return sigma;
+}
+
+// local padded dims used by the trd kernels
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+int trd_lda_pad(int nrl) { return round_up(nrl > 0 ? nrl : 1, TR); }
+int trd_ncl_pad(int ncl) { return round_up(ncl > 0 ? ncl : 1, TC * SW); }
+
+void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, int m_forward)
+{
+    Context &c = ctx();
+    const Grid &g = c.g;
+    cudaStream_t st = c.stream;
+    const int nrl = cyc_count(n, g.px, g.x), ncl = cyc_count(n, g.py, g.y);
+    EE_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * n, st));
+    EE_CUDA(cudaMemsetAsync(e_out, 0, sizeof(double) * n, st));
+    if (n == 1) {
+        if (g.x == 0 && g.y == 0) EE_CUDA(cudaMemcpyAsync(d_out, a_user, sizeof(double), cudaMemcpyDeviceToDevice, st));
+        comm_allreduce_sum(d_out, 1, COMM_WORLD, st);
+        return;
+    }
+    int m = m_forward < n ? m_forward : n;
+    if (m < 1) m = 1;
+    if (m > MAXM) m = MAXM;
+
+    // ---- internal padded copy of the local matrix ------------------------------------
+    const int lda = trd_lda_pad(nrl), nclp = trd_ncl_pad(ncl);
+    double *A = (double *)dev_alloc((size_t)lda * nclp * sizeof(double));
+    EE_CUDA(cudaMemsetAsync(A, 0, (size_t)lda * nclp * sizeof(double), st));
+    if (nrl > 0 && ncl > 0)
+        EE_CUDA(cudaMemcpy2DAsync(A, (size_t)lda * sizeof(double), a_user, (size_t)lda_user * sizeof(double),
+                                  (size_t)nrl * sizeof(double), ncl, cudaMemcpyDeviceToDevice, st));
+    {
+        dim3 grid((lda + 255) / 256, nclp);
+        zero_lower_kernel<<<grid, 256, 0, st>>>(A, lda, nclp, n, g.px, g.py, g.x, g.y);
+        EE_CHECK_LAUNCH();
+    }
+
+    // ---- workspace ---------------------------------------------------------------------
+    const int npad = round_up(n + 1, 256);
+    const int nstrip_max = (nclp + SW * TC - 1) / (SW * TC);
+    const int nbr_max = lda / TR;
+    const int maxvb = (n + VROWS) / VROWS + 1;
+    size_t wsz = 0;
+    auto take = [&](size_t cnt) { size_t o = wsz; wsz += (cnt + 31) & ~(size_t)31; return o; };
+    size_t oU = take((size_t)npad * m), oV = take((size_t)npad * m), oW = take((size_t)npad * m);
+    size_t oU1 = take(npad), oU2 = take(npad), oP = take(npad);
+    size_t oProw = take((size_t)nstrip_max * lda), oPcol = take((size_t)nbr_max * nclp);
+    size_t oDots = take((size_t)NCH * 2 * MAXM), oSt = take(2 * MAXM), oPart = take(2 * (size_t)maxvb);
+    size_t oScal = take(32), oTick = take(32);
+    size_t oUVx = take((size_t)lda * 2 * m), oVUy = take((size_t)nclp * 2 * m);
+    double *ws = (double *)dev_alloc(wsz * sizeof(double));
+    EE_CUDA(cudaMemsetAsync(ws, 0, wsz * sizeof(double), st));
+
+    TrdP P;
+    memset(&P, 0, sizeof P);
+    P.A = A; P.lda = lda; P.px = g.px; P.py = g.py; P.x = g.x; P.y = g.y;
+    P.n = n; P.npad = npad;
+    P.U = ws + oU; P.V = ws + oV; P.W = ws + oW;
+    P.ucur = ws + oU1; P.unext = ws + oU2; P.pbuf = ws + oP;
+    P.Prow = ws + oProw; P.Pcol = ws + oPcol; P.ldprow = lda; P.ldpcol = nclp;
+    P.dots_part = ws + oDots; P.st = ws + oSt; P.part = ws + oPart; P.scal = ws + oScal;
+    P.tickets = reinterpret_cast<unsigned int *>(ws + oTick);
+    P.d_out = d_out; P.e_out = e_out;
+    double *UVx = ws + oUVx, *VUy = ws + oVUy;
+    const bool multi = g.nnod > 1;
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float t_symv = 0.f, t_syr2k = 0.f;
+    if (c.profiling) { EE_CUDA(cudaEventCreate(&ev0)); EE_CUDA(cudaEventCreate(&ev1)); }
+
+    const int nblk = (n - 1) / m + 1;
+    for (int ib = nblk; ib >= 1; ib--) {
+        const int i_base = (ib - 1) * m;
+        const int m0 = (m < n - i_base) ? m : n - i_base;
+        const int k_stop = (i_base == 0) ? 2 : 0;
+        if (i_base + m0 - 1 < 2) {
+            // nothing to reflect (n == 2): fall through to the final step
+            break;
+        }
+        P.i_base = i_base; P.m0 = m0;
+        // panel load (+ zero U,V)
+        {
+            dim3 grid((npad + 255) / 256, m);
+            TrdP Q = P;
+            panel_load_kernel<<<grid, 256, 0, st>>>(Q, 1);
+            EE_CHECK_LAUNCH();
+            if (multi) comm_allreduce_sum(P.W, (size_t)npad * m0, COMM_WORLD, st);
+        }
+        // panel prologue: first column of the panel (slot m0-1) is the raw panel copy
+        {
+            TrdP Q = P;
+            Q.k = m0 - 1; Q.L = i_base + m0 - 1; Q.first = 1; Q.has_next = 1; Q.ndone = 0;
+            Q.unext = P.ucur;  // write straight into ucur
+            int nb = (Q.L + 1 + VROWS - 1) / VROWS;
+            vvec_kernel<<<nb, VROWS, 0, st>>>(Q);
+            EE_CHECK_LAUNCH();
+        }
+        for (int k = m0 - 1; k >= k_stop; k--) {
+            const int i = i_base + k, L = i;
+            TrdP Q = P;
+            Q.k = k; Q.L = L; Q.ndone = m0 - 1 - k; Q.first = 0;
+            Q.has_next = (k - 1 >= k_stop) ? 1 : 0;
+            // ---- SYMV --------------------------------------------------------------
+            const int nclL = cyc_count(L, g.py, g.y);
+            const int nsc = (nclL + SW * TC - 1) / (SW * TC);
+            int gx = (nsc + 1) / 2, gy = 0;
+            if (nsc > 0) {
+                // rows of the biggest strip + rows of the smallest
+                auto strip_rows_h = [&](int sc) {
+                    int tlast = std::min((sc + 1) * SW, (nclL + TC - 1) / TC) - 1;
+                    int clast = std::min((tlast + 1) * TC, nclL) - 1;
+                    if (clast < tlast * TC) return 0;
+                    long long cmax_g = (long long)clast * g.py + g.y;
+                    if (cmax_g <= g.x) return 0;
+                    return (int)((cmax_g - g.x - 1) / ((long long)TR * g.px)) + 1;
+                };
+                for (int bx = 0; bx < gx; bx++) {
+                    int s1 = nsc - 1 - bx, s2 = bx;
+                    int r = strip_rows_h(s1) + (s2 != s1 ? strip_rows_h(s2) : 0);
+                    if (r > gy) gy = r;
+                    if (bx > 2 && bx < gx - 3) bx = gx - 4;  // extremes decide (rows are monotone)
+                }
+            }
+            const int ntile_blocks = gx * gy;
+            const int nblocks = ntile_blocks + (Q.ndone > 0 ? NCH : 0);
+            if (c.profiling) EE_CUDA(cudaEventRecord(ev0, st));
+            if (nblocks > 0) {
+                symv_kernel<<<nblocks, 256, 0, st>>>(Q, gx > 0 ? gx : 1, ntile_blocks);
+                EE_CHECK_LAUNCH();
+            }
+            if (c.profiling) {
+                EE_CUDA(cudaEventRecord(ev1, st));
+                EE_CUDA(cudaEventSynchronize(ev1));
+                float ms; EE_CUDA(cudaEventElapsedTime(&ms, ev0, ev1)); t_symv += ms;
+            }
+            // ---- p, alpha --------------------------------------------------------------
+            const int nvb = (L + VROWS - 1) / VROWS;
+            if (!multi) {
+                pvec_kernel<0><<<nvb, VROWS, 0, st>>>(Q);
+                EE_CHECK_LAUNCH();
+            } else {
+                pvec_kernel<1><<<nvb, VROWS, 0, st>>>(Q);
+                EE_CHECK_LAUNCH();
+                comm_allreduce_sum(P.pbuf, L, COMM_WORLD, st);
+                pvec_kernel<2><<<nvb, VROWS, 0, st>>>(Q);
+                EE_CHECK_LAUNCH();
+            }
+            // ---- v, next column ------------------------------------------------------
+            vvec_kernel<<<nvb, VROWS, 0, st>>>(Q);
+            EE_CHECK_LAUNCH();
+            std::swap(P.ucur, P.unext);
+        }
+        // ---- panel end: reflectors back into A, trailing rank-2k update ----------------
+        {
+            TrdP Q = P;
+            dim3 grid((lda + 255) / 256, m0);
+            panel_restore_kernel<<<grid, 256, 0, st>>>(Q, k_stop);
+            EE_CHECK_LAUNCH();
+        }
+        if (ib > 1) {
+            const int nrl_b = cyc_count(i_base, g.px, g.x), ncl_b = cyc_count(i_base, g.py, g.y);
+            if (nrl_b > 0 && ncl_b > 0) {
+                TrdP Q = P;
+                int mx = nrl_b > ncl_b ? nrl_b : ncl_b;
+                dim3 grid((mx + 255) / 256, 2 * m);
+                pack_uv_kernel<<<grid, 256, 0, st>>>(Q, UVx, lda, nrl_b, VUy, nclp, ncl_b, m);
+                EE_CHECK_LAUNCH();
+                TriSpec tri; tri.mode = 1; tri.px = g.px; tri.py = g.py; tri.x = g.x; tri.y = g.y;
+                if (c.profiling) EE_CUDA(cudaEventRecord(ev0, st));
+                dgemm(st, 'N', 'T', nrl_b, ncl_b, 2 * m, -1.0, UVx, lda, VUy, nclp, 1.0, A, lda, tri);
+                if (c.profiling) {
+                    EE_CUDA(cudaEventRecord(ev1, st));
+                    EE_CUDA(cudaEventSynchronize(ev1));
+                    float ms; EE_CUDA(cudaEventElapsedTime(&ms, ev0, ev1)); t_syr2k += ms;
+                }
+            }
+        }
+    }
+    // ---- final 2x2 (trd_t8.F:188-219) -------------------------------------------------------
+    {
+        TrdP Q = P;
+        trd_final_kernel<<<1, 32, 0, st>>>(Q);
+        EE_CHECK_LAUNCH();
+        if (multi) comm_allreduce_sum(P.scal + 4, 3, COMM_WORLD, st);
+        trd_final_store_kernel<<<1, 32, 0, st>>>(Q);
+        EE_CHECK_LAUNCH();
+    }
+    // reflectors back to the caller's array
+    if (nrl > 0 && ncl > 0)
+        EE_CUDA(cudaMemcpy2DAsync(a_user, (size_t)lda_user * sizeof(double), A, (size_t)lda * sizeof(double),
+                                  (size_t)nrl * sizeof(double), ncl, cudaMemcpyDeviceToDevice, st));
+    EE_CUDA(cudaStreamSynchronize(st));
+    if (c.profiling) {
+        c.timings[5] = t_symv * 1e-3; c.timings[6] = t_syr2k * 1e-3;
+        cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    }
+    dev_free(ws);
+    dev_free(A);
+}
+
+}  // namespace ee

@@ -1,0 +1,143 @@
+/*
+ * eigenexa_b200.h -- C ABI of the B200-native EigenExa hot path.
+ *
+ * Drop-in boundary: the entry points below are what the reference's C binding
+ * (C/EigenExa.h:12-46, C/EigenExa.c) and its Fortran shims (C/EigenExa.fh:10-19,
+ * C/eigen_exa_interfaces.F90) expose for eigen_init / eigen_free / eigen_get_matdims /
+ * eigen_s / eigen_sx and the query helpers.  Argument meaning, defaults and the
+ * "silent return" error convention follow src/eigen_libs.F:70-216 and
+ * src/eigen_s.F:81-133.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Host arrays a, z use the reference's 2D cyclic layout (block size 1,
+ * src/eigen_libs0.F:1986-2166): local a(j_loc,i_loc) = A(global row
+ * (j_loc-1)*x_nnod+x_inod, global col (i_loc-1)*y_nnod+y_inod), column-major with
+ * leading dimension lda >= local row count.  Only the upper triangle of A is read;
+ * a is destroyed (a(1:3,1) = flop count, seconds, -1; src/eigen_s.F:284-295).
+ *
+ * The reference takes an MPI communicator.  This build has no MPI: ranks are one
+ * process per GPU and the collectives are NCCL, so eigen_init takes a small POD
+ * describing the rank and the NCCL bootstrap id instead (INTEGRATION.md shows the
+ * MPI shim a maintainer adds: MPI_Comm_rank/size + MPI_Bcast of the id).
+ */
+#ifndef EIGENEXA_B200_H
+#define EIGENEXA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EIGENEXA_B200_UNIQUE_ID_BYTES 128
+
+/* replaces the MPI_Comm argument of eigen_init (C/EigenExa.h:12) */
+typedef struct eigenexa_b200_comm {
+    int rank;             /* 0-based rank in the job                                */
+    int nranks;           /* number of ranks (= GPUs)                               */
+    int device;           /* CUDA device ordinal for this rank, -1: keep current    */
+    int reserved;
+    unsigned char unique_id[EIGENEXA_B200_UNIQUE_ID_BYTES]; /* ncclUniqueId made by
+                           eigenexa_b200_get_unique_id on rank 0 and broadcast by the
+                           host (ignored when nranks == 1)                           */
+} eigenexa_b200_comm_t;
+
+/* rank 0 fills id[128]; returns 0 on success */
+int eigenexa_b200_get_unique_id(unsigned char *id);
+
+/* ---- reference API (C/EigenExa.h) ------------------------------------------------ */
+/* eigen_init(comm, order): src/eigen_libs.F:70-104; order 'C' (default) or 'R'.
+ * comm == NULL means a single-rank job on the current device.                       */
+void eigen_init(const eigenexa_b200_comm_t *comm, const char *order);
+void eigen_free(void);                                       /* src/eigen_libs.F:204-216 */
+
+/* eigen_s / eigen_sx: src/eigen_libs.F:150-202, src/eigen_sx.F:30.  mode "A" (values +
+ * vectors), "N" (values only), "X" (values refined by bisection + vectors).          */
+void eigen_s(int n, int nvec, double *a, int lda, double *w, double *z, int ldz,
+             int m_forward, int m_backward, const char *mode);
+void eigen_sx(int n, int nvec, double *a, int lda, double *w, double *z, int ldz,
+              int m_forward, int m_backward, const char *mode);
+
+void eigen_get_version(int *version, char *date, char *vcode); /* eigen_libs0.F:175-188 */
+void eigen_get_procs(int *nnod, int *x_nnod, int *y_nnod);     /* eigen_libs0.F:1551-1600 */
+void eigen_get_id(int *inod, int *x_inod, int *y_inod);        /* 1-based ids            */
+void eigen_get_matdims(int n, int *nx, int *ny, int m_forward, int m_backward,
+                       const char *mode);                      /* eigen_libs.F:106-148   */
+void eigen_get_errinfo(int *info);                             /* eigen_libs0.F:1689-1698 */
+int64_t eigen_memory_internal(int n, int lda, int ldz, int m1, int m0); /* device bytes */
+
+/* index helpers, explicit (nnod, inod) forms: eigen_libs0.F:1816-2258 */
+int eigen_loop_start(int istart, int nnod, int inod);
+int eigen_loop_end(int iend, int nnod, int inod);
+int eigen_translate_l2g(int ictr, int nnod, int inod);
+int eigen_translate_g2l(int ictr, int nnod, int inod);
+int eigen_owner_node(int ictr, int nnod, int inod);
+int eigen_owner_index(int ictr, int nnod, int inod);
+
+/* ---- Fortran-77 style symbols the reference's C layer binds (C/EigenExa.fh:10-19):
+ * all arguments by reference, hidden string lengths ignored.                         */
+void eigen_libs_eigen_init_(const eigenexa_b200_comm_t *comm, const char *order);
+void eigen_libs_eigen_free_(void);
+void eigen_libs_eigen_s_(int *n, int *nvec, double *a, int *lda, double *w, double *z,
+                         int *ldz, int *m_forward, int *m_backward, const char *mode);
+void eigen_libs_eigen_sx_(int *n, int *nvec, double *a, int *lda, double *w, double *z,
+                          int *ldz, int *m_forward, int *m_backward, const char *mode);
+void eigen_libs_eigen_get_matdims_(int *n, int *nx, int *ny, int *m_forward,
+                                   int *m_backward, const char *mode);
+void eigen_libs0_eigen_get_version_(int *version, char *date, char *vcode);
+void eigen_libs0_eigen_get_procs_(int *nnod, int *x_nnod, int *y_nnod);
+void eigen_libs0_eigen_get_id_(int *inod, int *x_inod, int *y_inod);
+void eigen_libs0_eigen_get_errinfo_(int *info);
+
+/* ---- stage-level entry points (the reference's public module procedures) ----------
+ * eigen_trd(n,a,lda,d,e,m)                 src/eigen_trd.F:82
+ * eigen_common_trbakwy(n,nvec,a,lda,z,ldz,e,m,iblk)  src/trbakwy4.F:77
+ * Host arrays in the 2D cyclic layout; d, e, of length n are replicated outputs.
+ * Return 0 on success, nonzero on error (not initialised, bad arguments).            */
+int eigenexa_b200_trd(int n, double *a, int lda, double *d, double *e, int m_forward);
+int eigenexa_b200_trbakwy(int n, int nvec, const double *a, int lda, double *z, int ldz,
+                          const double *e, int m_backward);
+/* tridiagonal eigen-decomposition stage (eigen_dc2, src/dc2.F:78): d,e replicated in,
+ * w ascending out, z = local part of the eigenvector matrix in the 2D cyclic layout.  */
+int eigenexa_b200_dc(int n, int nvec, const double *d, const double *e, double *w,
+                     double *z, int ldz);
+/* eigenvalues only by Sturm bisection (eigen_bisect, src/bisect.F:67)                 */
+int eigenexa_b200_bisect(int n, const double *d, const double *e, double *w);
+
+/* ---- device-resident variant: a_dev / z_dev / w_dev are DEVICE pointers on this
+ * rank's GPU (same layout).  Used to time the path with inputs already in HBM.       */
+int eigenexa_b200_eigen_s_dev(int n, int nvec, double *a_dev, int lda, double *w_dev,
+                              double *z_dev, int ldz, int m_forward, int m_backward,
+                              const char *mode);
+
+/* ---- benchmark/mat_set.f generators, written straight into device or host memory:
+ * mtype 0 Frank, 1 Toeplitz, 2 random R+R^T (counter-based, seed), 3 Frank-2.        */
+int eigenexa_b200_mat_set_dev(int n, double *a_dev, int lda, int mtype, uint64_t seed);
+int eigenexa_b200_mat_set_host(int n, double *a, int lda, int mtype, uint64_t seed);
+/* benchmark/ev_test.f on device: out[0]=|AZ-ZW|_F/(N eps |A|_F), out[1]=|Z^TZ-I|_F/(N eps),
+ * out[2]=|A|_F; out must hold 4 doubles (single rank; a_dev holds the full symmetric matrix, upper triangle read)           */
+int eigenexa_b200_ev_test_dev(int n, int nvec, const double *a_dev, int lda,
+                              const double *w_dev, const double *z_dev, int ldz, double *out);
+
+/* the FP64 tensor-core (DMMA) GEMM the path is built on, BLAS dgemm argument order
+ * (replaces the dgemm calls at src/eigen_t1.F:285-295, src/trbakwy4_body.F:573,604,721);
+ * device pointers, column-major, asynchronous on the library stream.                  */
+int eigenexa_b200_dgemm_dev(char transa, char transb, int m, int n, int k, double alpha,
+                            const double *a_dev, int lda, const double *b_dev, int ldb,
+                            double beta, double *c_dev, int ldc);
+void eigenexa_b200_sync(void);      /* wait for the library stream                     */
+void *eigenexa_b200_stream(void);   /* cudaStream_t of the library (for event timing)  */
+
+/* ---- instrumentation ------------------------------------------------------------- */
+/* number of kernels this library launched since the last reset (bench gpu_launches)  */
+int64_t eigenexa_b200_launch_count(int reset);
+/* stage timings of the last eigen_s call on this rank, seconds (CUDA events):
+ * t[0]=h2d t[1]=scaling+trd t[2]=tridiagonal solver t[3]=back-transform t[4]=d2h
+ * t[5]=symv kernels total t[6]=syr2k kernels total (filled when profiling is on)      */
+void eigenexa_b200_last_timings(double *t, int nt);
+void eigenexa_b200_set_profiling(int on);
+const char *eigenexa_b200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EIGENEXA_B200_H */
