@@ -283,8 +283,9 @@ def last_timings():
     return t
 
 
-def set_profiling(on: bool):
-    lib().eigenexa_b200_set_profiling(int(on))
+def set_profiling(level: int):
+    """0 off; 1 async CUDA events around every symv / syr2k launch; 2 sync per kernel class (debug)."""
+    lib().eigenexa_b200_set_profiling(int(level))
 
 
 def last_error() -> str:

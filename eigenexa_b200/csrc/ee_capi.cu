@@ -204,7 +204,7 @@ static void eigen_s_impl(int n, int nvec, double *a, int lda, double *w, double 
             EE_CUDA(cudaMemcpyAsync(d_d, w_d, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
             int info = dc_dev(n, nv, d_d, e_d, w_d, z_d, ldz_d);
             c.errinfo = info;
-            ret2 = 1.0;  // flop count of the merges is not tracked; keeps ret positive (eigen_s.F:286)
+            ret2 = c.timings[13] > 0 ? c.timings[13] : 1.0;  // merge GEMM flops (mx_pdlaed1.F:291,304); > 0 keeps ret positive
             if (mode == 'X') bisect_dev(n, d_d, e_d, w_d);
             T.mark(3);
             // ---- back-transformation (eigen_s.F:245-248) ------------------------------------
@@ -543,7 +543,7 @@ void eigenexa_b200_last_timings(double *t, int nt)
 {
     for (int i = 0; i < nt && i < 16; i++) t[i] = ctx().timings[i];
 }
-void eigenexa_b200_set_profiling(int on) { ctx().profiling = on != 0; }
+void eigenexa_b200_set_profiling(int level) { ctx().profiling = level; }
 const char *eigenexa_b200_last_error(void) { return g_err; }
 
 }  // extern "C"

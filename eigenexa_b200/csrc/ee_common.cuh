@@ -63,7 +63,7 @@ struct Context {
     cudaStream_t stream2 = nullptr;  // copies / side work
     Comm *comm = nullptr;
     int errinfo = 0;
-    bool profiling = false;
+    int profiling = 0;  // 0 off; 1 async CUDA events around symv/syr2k launches; 2 sync per kernel class
     double timings[16] = {0};
     int sm_count = 148;
 };

@@ -23,6 +23,7 @@
 // All reductions have a fixed order: results are bit-reproducible run to run.
 #include "ee_common.cuh"
 #include "ee_comm.h"
+#include <chrono>
 
 namespace ee {
 
@@ -32,7 +33,6 @@ constexpr int TR = 128;     // tile rows (local)
 constexpr int TC = 64;      // tile cols (local)
 constexpr int SW = 4;       // sub-tiles swept per CTA along a row strip
 constexpr int NCH = 32;     // row chunks for the panel dot products
-constexpr int VROWS = 256;  // rows per CTA in the vector kernels
 constexpr int MAXM = 256;   // max panel width
 
 struct TrdP {
@@ -272,13 +272,19 @@ __global__ void __launch_bounds__(256, 2) symv_kernel(TrdP P, int gx, int ntile_
 // ---------------------------------------------------------------------------------------
 // p = A u (from partials) - U s - V t ; partial u^T p ; last CTA: alpha
 // MODE 0: fused (single rank)   MODE 1: partial only (write p_partial)   MODE 2: post-allreduce
+// Thread layout: 32 consecutive rows x 8 slices; a row's partial sums / panel corrections
+// are split over the 8 slices (independent loads in flight) and combined in fixed order.
 // ---------------------------------------------------------------------------------------
+constexpr int VR = 32;   // rows per CTA in the vector kernels
+constexpr int VS = 8;    // slices per row
+
 template <int MODE>
-__global__ void __launch_bounds__(VROWS) pvec_kernel(TrdP P)
+__global__ void __launch_bounds__(VR * VS) pvec_kernel(TrdP P)
 {
     __shared__ double s_st[2 * MAXM];
     __shared__ int s_nbr[1024];
-    __shared__ double s_red[VROWS / 32];
+    __shared__ double s_acc[VS][VR];
+    __shared__ double s_red[VR * VS / 32];
     __shared__ unsigned int s_last;
     const int nd = P.ndone;
     const int nclL = ncl_of(P);
@@ -290,41 +296,50 @@ __global__ void __launch_bounds__(VROWS) pvec_kernel(TrdP P)
         for (int c = threadIdx.x; c < 2 * nd; c += blockDim.x) s_st[c] = P.st[c];
     }
     __syncthreads();
-    const int g = blockIdx.x * VROWS + threadIdx.x;
-    double up = 0.0;
+    const int r = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int g = blockIdx.x * VR + r;
+    double acc = 0.0;
     if (g < P.L) {
-        double p = 0.0;
-        const double ug = P.ucur[g];
         if (MODE != 2) {
             const bool rown = (g % P.px) == P.x, coln = (g % P.py) == P.y;
             if (rown) {
                 const int jl = g / P.px, br = jl / TR;
-                for (int s = nsc - 1; s >= 0 && s_nbr[s] > br; s--) p += __ldcs(P.Prow + (size_t)s * P.ldprow + jl);
+                for (int s = nsc - 1 - sl; s >= 0 && s_nbr[s] > br; s -= VS) acc += __ldcs(P.Prow + (size_t)s * P.ldprow + jl);
             }
             if (coln) {
                 const int il = g / P.py;
                 const int nb = ntile_rows(P, il / TC, nclL);
-                for (int b = 0; b < nb; b++) p += __ldcs(P.Pcol + (size_t)b * P.ldpcol + il);
-                if (rown) p = fma(P.A[(size_t)il * P.lda + g / P.px], ug, p);
+                for (int b = sl; b < nb; b += VS) acc += __ldcs(P.Pcol + (size_t)b * P.ldpcol + il);
+                if (rown && sl == 0) acc = fma(P.A[(size_t)il * P.lda + g / P.px], P.ucur[g], acc);
             }
-        } else {
-            p = P.pbuf[g];
+        } else if (sl == 0) {
+            acc = P.pbuf[g];
         }
         if (MODE != 1) {
             // corrections with the finished pairs of this panel
-            for (int l = 0; l < nd; l++) {
+            for (int l = sl; l < nd; l += VS) {
                 const size_t off = (size_t)(P.k + 1 + l) * P.npad + g;
-                p = fma(-__ldg(P.U + off), s_st[l], p);
-                p = fma(-__ldg(P.V + off), s_st[nd + l], p);
+                acc = fma(-__ldg(P.U + off), s_st[l], acc);
+                acc = fma(-__ldg(P.V + off), s_st[nd + l], acc);
             }
-            up = ug * p;
         }
-        P.pbuf[g] = p;
+    }
+    s_acc[sl][r] = acc;
+    __syncthreads();
+    double up = 0.0;
+    if (sl == 0) {
+        double p = 0.0;
+#pragma unroll
+        for (int q = 0; q < VS; q++) p += s_acc[q][r];
+        if (g < P.L) {
+            P.pbuf[g] = p;
+            if (MODE != 1) up = P.ucur[g] * p;
+        }
+        up = warp_sum(up);
     }
     if (MODE == 1) return;
-    double bs = block_sum<VROWS>(up, s_red);
     if (threadIdx.x == 0) {
-        P.part[blockIdx.x] = bs;
+        P.part[blockIdx.x] = up;
         __threadfence();
         s_last = atomicAdd(&P.tickets[1], 1u);
     }
@@ -333,8 +348,8 @@ __global__ void __launch_bounds__(VROWS) pvec_kernel(TrdP P)
         __threadfence();
         double s = 0.0;
         for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) s += __ldcg(P.part + q);
-        // fixed-order tree: per-thread strided sums then block_sum (deterministic for a given grid)
-        double tot = block_sum<VROWS>(s, s_red);
+        // fixed order: per-thread strided sums then block_sum (deterministic for a given grid)
+        double tot = block_sum<VR * VS>(s, s_red);
         if (threadIdx.x == 0) {
             double beta = P.scal[2];
             P.scal[3] = tot / (2.0 * beta);  // alpha = u^T p / (2 beta)   (trd_t6_3.F:255-262)
@@ -347,23 +362,19 @@ __global__ void __launch_bounds__(VROWS) pvec_kernel(TrdP P)
 // v = (p - alpha u)/beta ; next raw column from the panel copy (left-looking) ; its norm;
 // last CTA: Householder scalars of the next column (trd_t2.F:574-614)
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(VROWS) vvec_kernel(TrdP P)
+__global__ void __launch_bounds__(VR * VS) vvec_kernel(TrdP P)
 {
-    __shared__ double s_ur[MAXM], s_vr[MAXM];  // row c of U and V for slots k..m0-1
-    __shared__ double s_red[VROWS / 32];
+    __shared__ double s_ur[MAXM], s_vr[MAXM];  // row c of U and V for slots lo..m0-1
+    __shared__ double s_acc[VS][VR];
+    __shared__ double s_red[VR * VS / 32];
     __shared__ unsigned int s_last;
     const int L = P.L, k = P.k;
     const int c = L - 1;  // next column (global), also the last row of u
     double alpha = 0.0, beta = 1.0;
-    int nl;               // pairs applied to the next column: slots lo..m0-1
-    int lo;
-    if (!P.first) {
-        alpha = P.scal[3]; beta = P.scal[2];
-        lo = k;
-    } else {
-        lo = k + 1;  // panel prologue: no pairs yet (k = m0 - 1 -> nl = 0)
-    }
-    nl = P.m0 - lo;
+    int lo;               // pairs applied to the next column: slots lo..m0-1
+    if (!P.first) { alpha = P.scal[3]; beta = P.scal[2]; lo = k; }
+    else lo = k + 1;      // panel prologue: no pairs yet (k = m0 - 1 -> nl = 0)
+    const int nl = P.m0 - lo;
     if (P.has_next) {
         for (int l = threadIdx.x; l < nl; l += blockDim.x) {
             int slot = lo + l;
@@ -379,39 +390,49 @@ __global__ void __launch_bounds__(VROWS) vvec_kernel(TrdP P)
         }
     }
     __syncthreads();
-    const int g = blockIdx.x * VROWS + threadIdx.x;
-    double nrm = 0.0;
-    // rows 0..L-1 carry u,v ; the next column has rows 0..c (row c = its diagonal)
+    const int r = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int g = blockIdx.x * VR + r;
+    const int kn = P.first ? k : k - 1;  // slot of the next column
+    const int top = P.first ? L : c;     // its diagonal row (= its reflector length)
+    double acc = 0.0;
     if (g < L || (P.first && g <= L)) {
         double ug = 0.0, vg = 0.0;
         if (!P.first) {
             ug = P.ucur[g];
             vg = (P.pbuf[g] - alpha * ug) / beta;
-            P.U[(size_t)k * P.npad + g] = ug;
-            P.V[(size_t)k * P.npad + g] = vg;
+            if (sl == 0) {
+                P.U[(size_t)k * P.npad + g] = ug;
+                P.V[(size_t)k * P.npad + g] = vg;
+            }
         }
-        if (P.has_next) {
-            const int kn = P.first ? k : k - 1;  // slot of the next column
-            const int top = P.first ? L : c;     // its diagonal row
-            if (g <= top) {
-                double a = P.W[(size_t)kn * P.npad + g];
-                for (int l = 0; l < nl; l++) {
-                    int slot = lo + l;
-                    double uj, vj;
-                    if (!P.first && slot == k) { uj = ug; vj = vg; }
-                    else { uj = __ldg(P.U + (size_t)slot * P.npad + g); vj = __ldg(P.V + (size_t)slot * P.npad + g); }
-                    a = fma(-uj, s_vr[l], a);
-                    a = fma(-vj, s_ur[l], a);
-                }
-                P.unext[g] = a;
-                if (g < top) nrm = a * a;
+        if (P.has_next && g <= top) {
+            if (sl == 0) acc = P.W[(size_t)kn * P.npad + g];
+            for (int l = sl; l < nl; l += VS) {
+                const int slot = lo + l;
+                double uj, vj;
+                if (!P.first && slot == k) { uj = ug; vj = vg; }
+                else { uj = __ldg(P.U + (size_t)slot * P.npad + g); vj = __ldg(P.V + (size_t)slot * P.npad + g); }
+                acc = fma(-uj, s_vr[l], acc);
+                acc = fma(-vj, s_ur[l], acc);
             }
         }
     }
     if (!P.has_next) return;
-    double bs = block_sum<VROWS>(nrm, s_red);
+    s_acc[sl][r] = acc;
+    __syncthreads();
+    double nrm = 0.0;
+    if (sl == 0) {
+        double a = 0.0;
+#pragma unroll
+        for (int q = 0; q < VS; q++) a += s_acc[q][r];
+        if (g <= top) {
+            P.unext[g] = a;
+            if (g < top) nrm = a * a;
+        }
+        nrm = warp_sum(nrm);
+    }
     if (threadIdx.x == 0) {
-        P.part[blockIdx.x] = bs;
+        P.part[blockIdx.x] = nrm;
         __threadfence();
         s_last = atomicAdd(&P.tickets[2], 1u);
     }
@@ -420,9 +441,8 @@ __global__ void __launch_bounds__(VROWS) vvec_kernel(TrdP P)
         __threadfence();
         double s = 0.0;
         for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) s += __ldcg(P.part + q);
-        double anorm2 = block_sum<VROWS>(s, s_red);
+        double anorm2 = block_sum<VR * VS>(s, s_red);
         if (threadIdx.x == 0) {
-            const int top = P.first ? L : c;  // next column index i' ; reflector length = top
             double a_n = __ldcg(P.unext + top - 1);
             double dia = __ldcg(P.unext + top);
             double g_n, u_n, bt;
@@ -451,7 +471,7 @@ __global__ void panel_load_kernel(TrdP P, int zero_first)
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= P.npad) return;
     double v = 0.0;
-    if (g <= gc && (gc % P.py) == P.y && (g % P.px) == P.x) v = P.A[(size_t)(gc / P.py) * P.lda + g / P.px];
+    if (k < P.m0 && g <= gc && (gc % P.py) == P.y && (g % P.px) == P.x) v = P.A[(size_t)(gc / P.py) * P.lda + g / P.px];
     P.W[(size_t)k * P.npad + g] = v;
     if (zero_first) { P.U[(size_t)k * P.npad + g] = 0.0; P.V[(size_t)k * P.npad + g] = 0.0; }
 }
@@ -636,7 +656,7 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
     const int npad = round_up(n + 1, 256);
     const int nstrip_max = (nclp + SW * TC - 1) / (SW * TC);
     const int nbr_max = lda / TR;
-    const int maxvb = (n + VROWS) / VROWS + 1;
+    const int maxvb = (n + VR) / VR + 2;
     size_t wsz = 0;
     auto take = [&](size_t cnt) { size_t o = wsz; wsz += (cnt + 31) & ~(size_t)31; return o; };
     size_t oU = take((size_t)npad * m), oV = take((size_t)npad * m), oW = take((size_t)npad * m);
@@ -662,8 +682,31 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
     const bool multi = g.nnod > 1;
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    float t_symv = 0.f, t_syr2k = 0.f;
+    float t_symv = 0.f, t_syr2k = 0.f, t_pvec = 0.f, t_vvec = 0.f;
     if (c.profiling) { EE_CUDA(cudaEventCreate(&ev0)); EE_CUDA(cudaEventCreate(&ev1)); }
+    // level 1: event pairs recorded without synchronising (read after the final sync)
+    std::vector<cudaEvent_t> pool_symv, pool_syr2k;
+    auto prof_begin = [&](int cls = 0) {
+        if (c.profiling >= 2) EE_CUDA(cudaEventRecord(ev0, st));
+        else if (c.profiling == 1 && cls) {
+            cudaEvent_t e; EE_CUDA(cudaEventCreate(&e)); EE_CUDA(cudaEventRecord(e, st));
+            (cls == 1 ? pool_symv : pool_syr2k).push_back(e);
+        }
+    };
+    auto prof_end = [&](float &acc, int cls = 0) {
+        if (c.profiling >= 2) {
+            EE_CUDA(cudaEventRecord(ev1, st));
+            EE_CUDA(cudaEventSynchronize(ev1));
+            float ms; EE_CUDA(cudaEventElapsedTime(&ms, ev0, ev1)); acc += ms;
+        } else if (c.profiling == 1 && cls) {
+            cudaEvent_t e; EE_CUDA(cudaEventCreate(&e)); EE_CUDA(cudaEventRecord(e, st));
+            (cls == 1 ? pool_symv : pool_syr2k).push_back(e);
+        }
+    };
+    auto wall = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tw0 = wall();
+    if (c.profiling >= 2) EE_CUDA(cudaStreamSynchronize(st));
+    double tw1 = wall();
 
     const int nblk = (n - 1) / m + 1;
     for (int ib = nblk; ib >= 1; ib--) {
@@ -688,8 +731,8 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
             TrdP Q = P;
             Q.k = m0 - 1; Q.L = i_base + m0 - 1; Q.first = 1; Q.has_next = 1; Q.ndone = 0;
             Q.unext = P.ucur;  // write straight into ucur
-            int nb = (Q.L + 1 + VROWS - 1) / VROWS;
-            vvec_kernel<<<nb, VROWS, 0, st>>>(Q);
+            int nb = (Q.L + 1 + VR - 1) / VR;
+            vvec_kernel<<<nb, VR * VS, 0, st>>>(Q);
             EE_CHECK_LAUNCH();
         }
         for (int k = m0 - 1; k >= k_stop; k--) {
@@ -715,36 +758,35 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
                     int s1 = nsc - 1 - bx, s2 = bx;
                     int r = strip_rows_h(s1) + (s2 != s1 ? strip_rows_h(s2) : 0);
                     if (r > gy) gy = r;
-                    if (bx > 2 && bx < gx - 3) bx = gx - 4;  // extremes decide (rows are monotone)
                 }
             }
             const int ntile_blocks = gx * gy;
             const int nblocks = ntile_blocks + (Q.ndone > 0 ? NCH : 0);
-            if (c.profiling) EE_CUDA(cudaEventRecord(ev0, st));
+            prof_begin(1);
             if (nblocks > 0) {
                 symv_kernel<<<nblocks, 256, 0, st>>>(Q, gx > 0 ? gx : 1, ntile_blocks);
                 EE_CHECK_LAUNCH();
             }
-            if (c.profiling) {
-                EE_CUDA(cudaEventRecord(ev1, st));
-                EE_CUDA(cudaEventSynchronize(ev1));
-                float ms; EE_CUDA(cudaEventElapsedTime(&ms, ev0, ev1)); t_symv += ms;
-            }
+            prof_end(t_symv, 1);
             // ---- p, alpha --------------------------------------------------------------
-            const int nvb = (L + VROWS - 1) / VROWS;
+            const int nvb = (L + VR - 1) / VR;
+            prof_begin();
             if (!multi) {
-                pvec_kernel<0><<<nvb, VROWS, 0, st>>>(Q);
+                pvec_kernel<0><<<nvb, VR * VS, 0, st>>>(Q);
                 EE_CHECK_LAUNCH();
             } else {
-                pvec_kernel<1><<<nvb, VROWS, 0, st>>>(Q);
+                pvec_kernel<1><<<nvb, VR * VS, 0, st>>>(Q);
                 EE_CHECK_LAUNCH();
                 comm_allreduce_sum(P.pbuf, L, COMM_WORLD, st);
-                pvec_kernel<2><<<nvb, VROWS, 0, st>>>(Q);
+                pvec_kernel<2><<<nvb, VR * VS, 0, st>>>(Q);
                 EE_CHECK_LAUNCH();
             }
+            prof_end(t_pvec);
+            prof_begin();
             // ---- v, next column ------------------------------------------------------
-            vvec_kernel<<<nvb, VROWS, 0, st>>>(Q);
+            vvec_kernel<<<nvb, VR * VS, 0, st>>>(Q);
             EE_CHECK_LAUNCH();
+            prof_end(t_vvec);
             std::swap(P.ucur, P.unext);
         }
         // ---- panel end: reflectors back into A, trailing rank-2k update ----------------
@@ -763,16 +805,14 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
                 pack_uv_kernel<<<grid, 256, 0, st>>>(Q, UVx, lda, nrl_b, VUy, nclp, ncl_b, m);
                 EE_CHECK_LAUNCH();
                 TriSpec tri; tri.mode = 1; tri.px = g.px; tri.py = g.py; tri.x = g.x; tri.y = g.y;
-                if (c.profiling) EE_CUDA(cudaEventRecord(ev0, st));
+                prof_begin(2);
                 dgemm(st, 'N', 'T', nrl_b, ncl_b, 2 * m, -1.0, UVx, lda, VUy, nclp, 1.0, A, lda, tri);
-                if (c.profiling) {
-                    EE_CUDA(cudaEventRecord(ev1, st));
-                    EE_CUDA(cudaEventSynchronize(ev1));
-                    float ms; EE_CUDA(cudaEventElapsedTime(&ms, ev0, ev1)); t_syr2k += ms;
-                }
+                prof_end(t_syr2k, 2);
             }
         }
     }
+    double tw2 = wall();
+    if (c.profiling >= 2) { EE_CUDA(cudaStreamSynchronize(st)); tw2 = wall(); }
     // ---- final 2x2 (trd_t8.F:188-219) -------------------------------------------------------
     {
         TrdP Q = P;
@@ -787,12 +827,26 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
         EE_CUDA(cudaMemcpy2DAsync(a_user, (size_t)lda_user * sizeof(double), A, (size_t)lda * sizeof(double),
                                   (size_t)nrl * sizeof(double), ncl, cudaMemcpyDeviceToDevice, st));
     EE_CUDA(cudaStreamSynchronize(st));
-    if (c.profiling) {
-        c.timings[5] = t_symv * 1e-3; c.timings[6] = t_syr2k * 1e-3;
-        cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    double tw3 = wall();
+    if (c.profiling == 1) {
+        auto drain = [&](std::vector<cudaEvent_t> &pool, float &acc) {
+            for (size_t i = 0; i + 1 < pool.size(); i += 2) {
+                float ms = 0.f; EE_CUDA(cudaEventElapsedTime(&ms, pool[i], pool[i + 1])); acc += ms;
+            }
+            for (cudaEvent_t e : pool) cudaEventDestroy(e);
+            pool.clear();
+        };
+        drain(pool_symv, t_symv); drain(pool_syr2k, t_syr2k);
     }
     dev_free(ws);
     dev_free(A);
+    double tw4 = wall();
+    if (c.profiling) {
+        c.timings[5] = t_symv * 1e-3; c.timings[6] = t_syr2k * 1e-3;
+        c.timings[7] = t_pvec * 1e-3; c.timings[8] = t_vvec * 1e-3;
+        c.timings[9] = tw1 - tw0; c.timings[10] = tw2 - tw1; c.timings[11] = tw3 - tw2; c.timings[12] = tw4 - tw3;
+        cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    }
 }
 
 }  // namespace ee

@@ -134,7 +134,7 @@ int64_t eigenexa_b200_launch_count(int reset);
  * t[0]=h2d t[1]=scaling+trd t[2]=tridiagonal solver t[3]=back-transform t[4]=d2h
  * t[5]=symv kernels total t[6]=syr2k kernels total (filled when profiling is on)      */
 void eigenexa_b200_last_timings(double *t, int nt);
-void eigenexa_b200_set_profiling(int on);
+void eigenexa_b200_set_profiling(int level); /* 0 off, 1 async events (symv, syr2k), 2 debug */
 const char *eigenexa_b200_last_error(void);
 
 #ifdef __cplusplus

@@ -1,0 +1,138 @@
+"""CPU: pins the oracle against the reference's known answers and LAPACK golden vectors."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden.npz"))
+F = lambda x: np.array(x, order="F", copy=True)
+
+
+@pytest.mark.parametrize("n", [10, 100, 1000])
+def test_frank_spectrum_known_answer(n):
+    """benchmark/mat_set.f:638-647 closed form; w_test.f:142 gate sqrt(eps)."""
+    a = O.mat_set(n, O.MAT_FRANK)
+    w, z = O.eigen_s(a)
+    ref = np.sort(G[f"frank_w_{n}"])
+    assert np.abs(w - ref).max() / np.abs(ref).max() < np.sqrt(O.EPS)
+    assert np.allclose(O.w_set(n, 0), G[f"frank_w_{n}"], rtol=1e-14)
+    rel, ab = O.w_test(w, 0)
+    assert rel < np.sqrt(O.EPS)
+
+
+def test_matdims_known_values():
+    for n, px, py, nx, ny in G["matdims"]:
+        assert O.get_matdims(int(n), int(px), int(py)) == (int(nx), int(ny))
+    # 32-bit guard of the reference: N=50000 on 1x1 / 1x2 and N=100000 on 2x4 are rejected
+    assert O.get_matdims(50000, 1, 1) == (-1, -1)
+    assert O.get_matdims(50000, 1, 2) == (-1, -1)
+    assert O.get_matdims(100000, 2, 4) == (-1, -1)
+    assert O.get_matdims(50000, 2, 2)[0] > 0
+    assert O.get_matdims(0) == (-1, -1)
+    assert O.get_matdims(1000, 2, 2, mode="M") == (500, 500)
+    assert O.get_matdims(1000, 2, 2, mode="L") == (512, 500)
+
+
+def test_grid_shapes():
+    """eigen_libs0.F:526-540: 1->1x1, 2->1x2, 4->2x2, 8->2x4."""
+    assert [O.grid_dims(p) for p in (1, 2, 4, 8, 6, 16)] == [(1, 1), (1, 2), (2, 2), (2, 4), (2, 3), (4, 4)]
+    assert O.grid_coords(3, 2, 4, "C") == (1, 2)
+    assert O.grid_coords(3, 2, 4, "R") == (1, 3)
+
+
+def test_c_test_2x2():
+    a = np.array([[-2.0, 1.0], [1.0, -2.0]], order="F")
+    w, z = O.eigen_s(a, m_f=1, m_b=1)
+    assert np.allclose(w, G["ctest_w"], atol=1e-15)
+    assert np.allclose(np.abs(z), np.sqrt(0.5))
+
+
+@pytest.mark.parametrize("n,mt", [(64, 2), (200, 0), (333, 2), (150, 3), (120, 1)])
+def test_trd_against_lapack_golden(n, mt):
+    """dsytrd('U') uses the same sign convention g = -sign(|a|, a_L); only e(2) differs in sign
+    (reference reflects the last 1-vector, eigen_trd_t8.F:190-199) -> compare d and |e|."""
+    a = O.mat_set(n, mt)
+    chk = G[f"mat_{n}_{mt}_checksum"]
+    assert np.allclose([a.sum(), np.abs(a).max(), a[0, -1], a[n // 2, n // 3]], chk, rtol=1e-13)
+    nrm = np.linalg.norm(O.sym_from_upper(a))
+    for mf in (48, 7, 1):
+        d, e = O.trd(F(a), mf)
+        tol = 10 * n * O.EPS * nrm
+        assert np.abs(d - G[f"sytrd_d_{n}_{mt}"]).max() <= tol
+        assert np.abs(np.abs(e[1:]) - G[f"sytrd_abs_e_{n}_{mt}"]).max() <= tol
+        assert e[0] == 0.0
+    w, z = O.eigen_s(F(a))
+    assert np.abs(w - G[f"eig_w_{n}_{mt}"]).max() <= tol
+    res, orth = O.ev_test(O.sym_from_upper(a), w, z)
+    assert res < 10 and orth < 10          # BASELINE.json gates; reference gates are 768 / 8
+
+
+@pytest.mark.parametrize("mt", [4, 5, 6, 8])
+def test_helmert_families(mt):
+    """mat_set.f:337-454: A = H diag(w) H^T has the prescribed spectrum."""
+    n = 150
+    a = O.mat_set(n, mt)
+    w, z = O.eigen_s(F(a))
+    rel, ab = O.w_test(w, mt)
+    assert ab < np.sqrt(O.EPS) * max(1.0, np.abs(w).max())
+    res, orth = O.ev_test(O.sym_from_upper(a), w, z)
+    assert res < 10 and orth < 10
+
+
+def test_modes_and_edge_cases():
+    n = 120
+    a = O.mat_set(n, 2)
+    full = O.sym_from_upper(a)
+    wl = np.linalg.eigvalsh(full)
+    tol = 10 * n * O.EPS * np.linalg.norm(full)
+    wn, zn = O.eigen_s(F(a), mode="N")
+    assert zn is None and np.abs(wn - wl).max() <= tol
+    w5, z5 = O.eigen_s(F(a), nvec=5)
+    assert z5.shape == (n, 5)
+    assert np.linalg.norm(full @ z5 - z5 * w5[:5]) <= 10 * n * O.EPS * np.linalg.norm(full) * n
+    b = F(a); b[2, 5] = np.inf
+    wb, _ = O.eigen_s(b)
+    assert np.all(np.isnan(wb))
+    w1, z1 = O.eigen_s(np.array([[3.5]], order="F"))
+    assert w1[0] == 3.5 and z1[0, 0] == 1.0
+    # block sizes that do not divide n, m=1, m=2
+    for mf, mb in ((1, 1), (2, 3), (47, 129), (500, 500)):
+        w, z = O.eigen_s(F(a), m_f=mf, m_b=mb)
+        res, orth = O.ev_test(full, w, z)
+        assert np.abs(w - wl).max() <= tol and res < 10 and orth < 10
+
+
+def test_index_algebra_properties():
+    """eigen_libs0.F:1816-2258: l2g/g2l round trip, owner, loop_start/end partition."""
+    for nnod in (1, 2, 3, 4, 7):
+        n = 53
+        seen = np.zeros(n + 1, dtype=int)
+        for inod in range(1, nnod + 1):
+            ls, le = O.loop_start(1, nnod, inod), O.loop_end(n, nnod, inod)
+            for l in range(ls, le + 1):
+                g = O.translate_l2g(l, nnod, inod)
+                assert 1 <= g <= n
+                assert O.translate_g2l(g, nnod, inod) == l
+                assert O.owner_node(g, nnod, inod) == inod
+                assert O.owner_index(g, nnod, inod) == l
+                seen[g] += 1
+        assert np.all(seen[1:] == 1)
+        for g in range(1, n + 1):
+            owners = [i for i in range(1, nnod + 1) if O.owner_index(g, nnod, i) > 0]
+            assert owners == [O.owner_node(g, nnod, 1)]
+
+
+def test_cyclic_scatter_gather_roundtrip():
+    n = 37
+    a = O.mat_set(n, 2)
+    for px, py in ((1, 2), (2, 2), (2, 4), (3, 2)):
+        parts = {}
+        for x in range(1, px + 1):
+            for y in range(1, py + 1):
+                loc = O.scatter_cyclic(a, px, py, x, y)
+                gen = O.mat_set_local(n, 2, px, py, x, y)
+                assert np.array_equal(loc, gen)
+                parts[(x, y)] = loc
+        assert np.array_equal(O.gather_cyclic(parts, n, n, px, py), a)

@@ -47,14 +47,26 @@ ns = [int(v) for v in sys.argv[1:]] or [4000]
 for n in ns:
     a = np.zeros((n, n), order="F")
     E.mat_set_host(n, a, 2, 1)
-    E.set_profiling(False)
+    E.set_profiling(0)
     t0 = time.perf_counter(); d, e = E.eigen_trd(n, a.copy(order="F")); t1 = time.perf_counter() - t0
     t0 = time.perf_counter(); d, e = E.eigen_trd(n, a.copy(order="F")); t1 = time.perf_counter() - t0
-    E.set_profiling(True)
+    E.set_profiling(2)
     E.eigen_trd(n, a.copy(order="F"))
     tm = E.last_timings()
     symv_bytes = 8.0 * sum((i * (i - 1)) / 2 for i in range(2, n))
     r = {"n": n, "trd_wall_s": t1, "symv_s(profiled)": tm[5], "symv_GBs": symv_bytes / tm[5] / 1e9,
-         "syr2k_s": tm[6], "syr2k_tflops": (2.0 / 3.0) * n**3 / max(tm[6], 1e-9) / 1e12, "launches": E.launch_count(True)}
+         "syr2k_s": tm[6], "syr2k_tflops": (2.0 / 3.0) * n**3 / max(tm[6], 1e-9) / 1e12, "pvec_s": tm[7], "vvec_s": tm[8],
+         "host_alloc_s": tm[9], "host_loop_s": tm[10], "host_tail_s": tm[11], "host_free_s": tm[12], "launches": E.launch_count(True)}
     print(json.dumps(r)); sys.stdout.flush()
+E.eigen_free()
+
+E.eigen_init(None, "C")
+for n in ns:
+    a = np.zeros((n, n), order="F"); E.mat_set_host(n, a, 2, 1)
+    w = np.zeros(n); z = np.zeros((n, n), order="F")
+    E.set_profiling(0)
+    E.eigen_s(n, a.copy(order="F"), w, z)
+    t0 = time.perf_counter(); E.eigen_s(n, a.copy(order="F"), w, z); t1 = time.perf_counter() - t0
+    tm = E.last_timings()
+    print(json.dumps({"n": n, "eigen_s_wall_s": t1, "h2d": tm[0], "trd": tm[1], "dc": tm[2], "trbak": tm[3], "d2h": tm[4]}))
 E.eigen_free()
