@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the eigen_s hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--n 50000] [--impl reference]
+    (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+One "step" = one eigen_s solve (scaling, Householder tridiagonalisation, tridiagonal D&C,
+compact-WY back-transformation) of the BASELINE.json headline workload: N = 50000 random
+symmetric FP64, all eigenpairs (configs[3]); strong scaling over a 2D cyclic grid.
+  value  : FP64 TFLOP/s with A already resident in HBM (reference flop convention
+           4/3 n^3 + merge-GEMM flops + 2 nvec n^2, src/eigen_s.F:177,248,270)
+  e2e    : same metric through the reference-facing C-ABI call eigen_s(...) with HOST (pinned)
+           buffers: H2D of A and D2H of w, Z inside the timed region
+  roofline: dominant kernel = symv_kernel (SYMV over the upper triangle, HBM bound), timed
+           live with CUDA events on the library stream around every launch of the timed steps
+  cpu_baseline / --impl reference: the oracle (C/OpenMP restatement of the reference algorithm
+           + LAPACK dstevd) on the box's host cores, on a bounded sample.  The reference
+           itself (Fortran + MPI + ScaLAPACK) cannot be built in this image.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+EPS = 2.0 ** -52
+
+
+def flops_model(n, nvec, dc_flops=0.0):
+    return 4.0 / 3.0 * n ** 3 + dc_flops + 2.0 * nvec * float(n) ** 2
+
+
+def symv_bytes(n):
+    # strict upper triangle of the trailing L x L matrix, once per column
+    return 8.0 * sum(L * (L - 1) // 2 for L in range(2, n))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        time.sleep(0.1)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").replace("-", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(len(r) >= 9 and r[5 + i].lower() == "active" for r in self.rows)]
+        busy = [v for v in sm if v > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def cpu_oracle_leg(n_s, steps=1, warmup=0):
+    """Times the oracle eigen_s (the CPU path) on a bounded sample; returns (TFLOP/s, seconds, cores)."""
+    import numpy as np
+    from oracle import oracle as O
+    a0 = O.mat_set(n_s, O.MAT_RANDOM)
+    for _ in range(warmup):
+        O.eigen_s(np.array(a0, order="F"))
+    t = []
+    for _ in range(max(1, steps)):
+        a = np.array(a0, order="F")
+        t0 = time.perf_counter()
+        w, z = O.eigen_s(a)
+        t.append(time.perf_counter() - t0)
+    sec = sum(t) / len(t)
+    return flops_model(n_s, n_s) / sec / 1e12, sec, os.cpu_count()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_s = args.cpu_n
+    tf, sec, cores = cpu_oracle_leg(n_s, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "eigen_s_fp64_tflops", "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"eigen_s N={args.n} random symmetric FP64, all eigenpairs (BASELINE configs[3])",
+                   "n": args.n, "nvec": args.n, "m_forward": 48, "m_backward": 128, "mode": "A"},
+        "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port",
+                         "sample": f"eigen_s N={n_s} random symmetric, all eigenpairs, {sec:.2f} s per solve; oracle = "
+                                   "C/OpenMP restatement of the reference algorithm + LAPACK dstevd (the Fortran/MPI/"
+                                   "ScaLAPACK reference cannot be built in this image); TFLOP/s is size-normalised"},
+        "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--n", type=int, default=int(os.environ.get("EIGENEXA_BENCH_N", "50000")))
+    ap.add_argument("--cpu-n", type=int, default=3000, help="size of the bounded CPU sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import eigenexa_b200 as E
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    E.eigen_init_torch("C")
+    nnod, px, py = E.eigen_get_procs()
+    inod, xi, yi = E.eigen_get_id()
+    if nnod != world:
+        raise SystemExit("eigen_init failed: " + E.last_error())
+
+    n = args.n
+    nvec = n
+    nrl = E.eigen_loop_end(n, px, xi)
+    ncl = E.eigen_loop_end(n, py, yi)
+    nvl = E.eigen_loop_end(nvec, py, yi)
+    lda = max(nrl, 1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        E.sync()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- synthetic input, generated on the device (benchmark/mat_set.f type 2, counter-based) ----
+    a_master = torch.empty((max(ncl, 1), lda), dtype=torch.float64, device=dev)  # column-major lda x ncl
+    E.mat_set_dev(n, a_master.data_ptr(), lda, 2, 1)
+    a_work = torch.empty_like(a_master)
+    w_dev = torch.empty(n, dtype=torch.float64, device=dev)
+    z_dev = torch.empty((max(nvl, 1), lda), dtype=torch.float64, device=dev)
+    lib_stream = torch.cuda.ExternalStream(E.stream_ptr(), device=dev)
+
+    def step_dev():
+        a_work.copy_(a_master)          # the solver destroys a; restoring it is part of the step (D2D, ~ms)
+        torch.cuda.current_stream().synchronize()
+        E.eigen_s_dev(n, a_work.data_ptr(), lda, w_dev.data_ptr(), z_dev.data_ptr(), lda, nvec=nvec,
+                      m_forward=48, m_backward=128, mode="A")
+
+    # ---- leg 1: inputs resident in HBM ---------------------------------------------------------
+    for _ in range(args.warmup):
+        step_dev()
+    E.set_profiling(1)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    E.launch_count(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(lib_stream)
+    t0 = time.perf_counter()
+    stage = np.zeros(16)
+    for _ in range(args.steps):
+        step_dev()
+        stage += E.last_timings()
+    ev1.record(lib_stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_s = ev0.elapsed_time(ev1) * 1e-3
+    launches = E.launch_count(True)
+    clocks = sampler.stop() if rank == 0 else None
+    E.set_profiling(0)
+    t_step = max_over_ranks(max(dev_s, 0.0) if dev_s > 0 else wall) / args.steps
+    stage /= args.steps
+    dc_flops = float(stage[13])
+    flops = flops_model(n, nvec, dc_flops)
+    value = flops / t_step / 1e12
+
+    # parity of the timed result, size-independent property (ev_test on device, single rank only)
+    check = None
+    if world == 1 and n <= 60000:
+        try:
+            res, orth = E.ev_test_dev(n, nvec, a_master.data_ptr(), lda, w_dev.data_ptr(), z_dev.data_ptr(), lda)
+            check = {"residual_over_n_eps_normA": res, "orth_over_n_eps": orth, "gate": 10}
+        except Exception as ex:  # noqa: BLE001
+            check = {"error": str(ex)}
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    symv_s = float(stage[5])
+    bytes_rank = symv_bytes(n) / world
+    n_symv = max(n - 2, 1)
+    achieved = bytes_rank / symv_s / 1e9 if symv_s > 0 else None
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "symv_ncu_traffic.json"))).get("traffic_bytes_per_launch")
+    except Exception:
+        pass
+    fp64_peak = 35.4
+    try:
+        fp64_peak = float(json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))["cublas_dgemm_tflops"])
+    except Exception:
+        pass
+    roofline = {"kernel": "symv_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "launches_per_step": n_symv, "avg_launch_ms": symv_s / n_symv * 1e3,
+                "algorithmic_bytes_per_launch_avg": bytes_rank / n_symv,
+                "timing": "CUDA events on the library stream around every launch of the timed steps"}
+    stages = {"h2d_s": float(stage[0]), "trd_s": float(stage[1]), "dc_s": float(stage[2]), "trbak_s": float(stage[3]),
+              "symv_s": symv_s, "syr2k_s": float(stage[6]),
+              "syr2k_tflops": (2.0 / 3.0 * n ** 3 / world) / float(stage[6]) / 1e12 if stage[6] > 0 else None,
+              "trbak_tflops": (2.0 * nvec * float(n) ** 2 / world) / float(stage[3]) / 1e12 if stage[3] > 0 else None,
+              "fp64_tensor_peak_tflops": fp64_peak, "fp64_peak_source": "cuBLAS DGEMM 8192^3 measured on this pool"}
+
+    # ---- leg 2: end to end through eigen_s() with host buffers ------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h2d = nrl * ncl * 8
+        d2h = nrl * nvl * 8 + n * 8
+        try:
+            a_host = torch.empty((max(ncl, 1), lda), dtype=torch.float64, pin_memory=True)
+            z_host = torch.empty((max(nvl, 1), lda), dtype=torch.float64, pin_memory=True)
+            pinned = True
+        except Exception:
+            a_host = torch.empty((max(ncl, 1), lda), dtype=torch.float64)
+            z_host = torch.empty((max(nvl, 1), lda), dtype=torch.float64)
+            pinned = False
+        a_host.copy_(a_master)
+        head = a_host.view(-1)[:3].clone()
+        w_host = np.zeros(n)
+        del a_work, z_dev
+        torch.cuda.empty_cache()
+        a_np, z_np = a_host.numpy().T, z_host.numpy().T      # column-major views (lda x ncl)
+
+        def step_host():
+            a_host.view(-1)[:3] = head                        # eigen_s overwrites a(1:3,1) with its statistics
+            E.eigen_s(n, a_np, w_host, z_np, nvec=nvec, m_forward=48, m_backward=128, mode="A")
+
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()
+        barrier()
+        t_e2e = max_over_ranks(time.perf_counter() - t0) / args.steps
+        e2e = {"value": flops / t_e2e / 1e12, "unit": "TFLOP/s", "time_s": t_e2e, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "pinned": pinned,
+               "api": "eigen_s(n, nvec, a, lda, w, z, ldz, m_forward, m_backward, mode) with host arrays"}
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        tf, sec, cores = cpu_oracle_leg(args.cpu_n)
+        cpu = {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port",
+               "sample": f"eigen_s N={args.cpu_n} random symmetric, all eigenpairs: {sec:.2f} s (oracle C/OpenMP + LAPACK "
+                         f"dstevd); extrapolated to N={n} by n^3: {sec * (n / args.cpu_n) ** 3:.0f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": "eigen_s_fp64_tflops", "value": value, "unit": "TFLOP/s", "time_s": t_step, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"eigen_s N={n} random symmetric FP64, all eigenpairs (BASELINE configs[3])", "n": n,
+                       "nvec": nvec, "m_forward": 48, "m_backward": 128, "mode": "A", "grid": f"{px}x{py}",
+                       "l2": f"inputs larger than L2 (A = {nrl * ncl * 8 / 1e9:.1f} GB per GPU vs 126 MB)",
+                       "flop_model": "4/3 n^3 + merge GEMM flops + 2 nvec n^2 (src/eigen_s.F:177,248,270)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "stages": stages,
+            "cpu_baseline": cpu, "parity_check": check,
+        }
+        print(json.dumps(line), flush=True)
+    E.eigen_free()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -73,6 +73,7 @@ def lib() -> C.CDLL:
         L.eigenexa_b200_launch_count.restype = C.c_int64
         L.eigenexa_b200_last_timings.argtypes = [dp, C.c_int]
         L.eigenexa_b200_set_profiling.argtypes = [C.c_int]
+        L.eigenexa_b200_symv_trace.argtypes = [C.POINTER(C.c_float), C.c_int]
         L.eigenexa_b200_last_error.restype = C.c_char_p
         _lib = L
     return _lib
@@ -286,6 +287,14 @@ def last_timings():
 def set_profiling(level: int):
     """0 off; 1 async CUDA events around every symv / syr2k launch; 2 sync per kernel class (debug)."""
     lib().eigenexa_b200_set_profiling(int(level))
+
+
+def symv_trace():
+    """Per-launch symv_kernel milliseconds of the last eigen_trd (column n first)."""
+    cap = lib().eigenexa_b200_symv_trace(None, 0)
+    out = np.zeros(max(cap, 1), dtype=np.float32)
+    lib().eigenexa_b200_symv_trace(out.ctypes.data_as(C.POINTER(C.c_float)), cap)
+    return out[:cap]
 
 
 def last_error() -> str:

@@ -308,6 +308,8 @@ void eigen_free(void)
     if (!c.initialized) return;
     cudaStreamSynchronize(c.stream);
     comm_finalize();
+    for (cudaEvent_t e : c.ev_pool) cudaEventDestroy(e);
+    c.ev_pool.clear();
     cudaStreamDestroy(c.stream); cudaStreamDestroy(c.stream2);
     c.stream = c.stream2 = nullptr;
     c.initialized = false;
@@ -542,6 +544,14 @@ int64_t eigenexa_b200_launch_count(int reset)
 void eigenexa_b200_last_timings(double *t, int nt)
 {
     for (int i = 0; i < nt && i < 16; i++) t[i] = ctx().timings[i];
+}
+/* per-column symv kernel milliseconds of the last eigen_trd (column n-1 first); returns count */
+int eigenexa_b200_symv_trace(float *out, int cap)
+{
+    const std::vector<float> &t = ctx().symv_trace;
+    int cnt = (int)t.size() < cap ? (int)t.size() : cap;
+    for (int i = 0; i < cnt; i++) out[i] = t[i];
+    return (int)t.size();
 }
 void eigenexa_b200_set_profiling(int level) { ctx().profiling = level; }
 const char *eigenexa_b200_last_error(void) { return g_err; }

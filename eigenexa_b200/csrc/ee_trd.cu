@@ -686,10 +686,16 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
     if (c.profiling) { EE_CUDA(cudaEventCreate(&ev0)); EE_CUDA(cudaEventCreate(&ev1)); }
     // level 1: event pairs recorded without synchronising (read after the final sync)
     std::vector<cudaEvent_t> pool_symv, pool_syr2k;
+    size_t pool_next = 0;
+    auto pool_get = [&]() {
+        if (pool_next == c.ev_pool.size()) { cudaEvent_t e; EE_CUDA(cudaEventCreate(&e)); c.ev_pool.push_back(e); }
+        return c.ev_pool[pool_next++];
+    };
+    c.symv_trace.clear();
     auto prof_begin = [&](int cls = 0) {
         if (c.profiling >= 2) EE_CUDA(cudaEventRecord(ev0, st));
         else if (c.profiling == 1 && cls) {
-            cudaEvent_t e; EE_CUDA(cudaEventCreate(&e)); EE_CUDA(cudaEventRecord(e, st));
+            cudaEvent_t e = pool_get(); EE_CUDA(cudaEventRecord(e, st));
             (cls == 1 ? pool_symv : pool_syr2k).push_back(e);
         }
     };
@@ -698,8 +704,9 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
             EE_CUDA(cudaEventRecord(ev1, st));
             EE_CUDA(cudaEventSynchronize(ev1));
             float ms; EE_CUDA(cudaEventElapsedTime(&ms, ev0, ev1)); acc += ms;
+            if (cls == 1) c.symv_trace.push_back(ms);
         } else if (c.profiling == 1 && cls) {
-            cudaEvent_t e; EE_CUDA(cudaEventCreate(&e)); EE_CUDA(cudaEventRecord(e, st));
+            cudaEvent_t e = pool_get(); EE_CUDA(cudaEventRecord(e, st));
             (cls == 1 ? pool_symv : pool_syr2k).push_back(e);
         }
     };
@@ -829,14 +836,14 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
     EE_CUDA(cudaStreamSynchronize(st));
     double tw3 = wall();
     if (c.profiling == 1) {
-        auto drain = [&](std::vector<cudaEvent_t> &pool, float &acc) {
+        auto drain = [&](std::vector<cudaEvent_t> &pool, float &acc, bool trace) {
             for (size_t i = 0; i + 1 < pool.size(); i += 2) {
                 float ms = 0.f; EE_CUDA(cudaEventElapsedTime(&ms, pool[i], pool[i + 1])); acc += ms;
+                if (trace) c.symv_trace.push_back(ms);
             }
-            for (cudaEvent_t e : pool) cudaEventDestroy(e);
             pool.clear();
         };
-        drain(pool_symv, t_symv); drain(pool_syr2k, t_syr2k);
+        drain(pool_symv, t_symv, true); drain(pool_syr2k, t_syr2k, false);
     }
     dev_free(ws);
     dev_free(A);

@@ -135,6 +135,9 @@ int64_t eigenexa_b200_launch_count(int reset);
  * t[5]=symv kernels total t[6]=syr2k kernels total (filled when profiling is on)      */
 void eigenexa_b200_last_timings(double *t, int nt);
 void eigenexa_b200_set_profiling(int level); /* 0 off, 1 async events (symv, syr2k), 2 debug */
+/* per-launch symv_kernel milliseconds of the last eigen_trd (first entry = column n);
+ * needs profiling >= 1; returns the number of launches recorded                        */
+int eigenexa_b200_symv_trace(float *out, int cap);
 const char *eigenexa_b200_last_error(void);
 
 #ifdef __cplusplus

@@ -1,0 +1,42 @@
+"""Multi-rank parity run (one process per GPU):  torchrun --nproc-per-node P tools/run_multi.py N [mtype]
+Each rank builds its 2D-cyclic part, calls eigen_s through the C ABI with host arrays, rank 0 gathers
+w, Z and checks them against the oracle / ev_test.  Prints one JSON line on rank 0."""
+import json, os, sys, time
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import eigenexa_b200 as E
+from oracle import oracle as O
+
+n = int(sys.argv[1]); mtype = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+mode = sys.argv[3] if len(sys.argv) > 3 else "A"
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+E.eigen_init_torch("C")
+nnod, px, py = E.eigen_get_procs(); inod, xi, yi = E.eigen_get_id()
+assert nnod == world, E.last_error()
+nx, ny = E.eigen_get_matdims(n)
+a = O.mat_set_local(n, mtype, px, py, xi, yi, lda=nx, ncols=ny)
+w = np.zeros(n); z = np.zeros((nx, ny), order="F")
+dist.barrier(); t0 = time.perf_counter()
+E.eigen_s(n, a, w, z, mode=mode)
+dist.barrier(); t1 = time.perf_counter() - t0
+parts = [None] * world if rank == 0 else None
+nr, nc = E.eigen_loop_end(n, px, xi), E.eigen_loop_end(n, py, yi)
+dist.gather_object(((xi, yi), z[:nr, :nc].copy(), w.copy()), parts, dst=0)
+if rank == 0:
+    ws = [p[2] for p in parts]
+    assert all(np.array_equal(ws[0], v) for v in ws), "w differs between ranks"
+    full = O.sym_from_upper(O.mat_set(n, mtype))
+    wl = np.linalg.eigvalsh(full)
+    out = {"n": n, "grid": f"{px}x{py}", "mode": mode, "seconds": t1,
+           "w_err_over_tol": float(np.abs(w - wl).max() / (10 * n * O.EPS * np.linalg.norm(full)))}
+    if mode != "N":
+        Z = O.gather_cyclic({p[0]: p[1] for p in parts}, n, n, px, py)
+        res, orth = O.ev_test(full, w, Z)
+        out.update({"residual": res, "orth": orth})
+    print(json.dumps(out), flush=True)
+E.eigen_free()
+dist.destroy_process_group()
