@@ -297,5 +297,9 @@ def symv_trace():
     return out[:cap]
 
 
+def set_debug_maxcols(ncols: int):
+    lib().eigenexa_b200_set_debug_maxcols(int(ncols))
+
+
 def last_error() -> str:
     return lib().eigenexa_b200_last_error().decode()

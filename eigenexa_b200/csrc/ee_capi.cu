@@ -553,6 +553,7 @@ int eigenexa_b200_symv_trace(float *out, int cap)
     for (int i = 0; i < cnt; i++) out[i] = t[i];
     return (int)t.size();
 }
+void eigenexa_b200_set_debug_maxcols(int ncols) { ctx().debug_maxcols = ncols; }
 void eigenexa_b200_set_profiling(int level) { ctx().profiling = level; }
 const char *eigenexa_b200_last_error(void) { return g_err; }
 

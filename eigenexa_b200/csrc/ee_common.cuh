@@ -66,6 +66,7 @@ struct Context {
     int profiling = 0;  // 0 off; 1 async CUDA events around symv/syr2k launches; 2 sync per kernel class
     double timings[16] = {0};
     int sm_count = 148;
+    int debug_maxcols = 0;              // > 0: eigen_trd stops after this many columns (profiling aid)
     std::vector<cudaEvent_t> ev_pool;   // reusable timing events (profiling level 1)
     std::vector<float> symv_trace;      // per-column symv milliseconds of the last trd (profiling >= 1)
 };

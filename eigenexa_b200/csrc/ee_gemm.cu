@@ -136,6 +136,31 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) dgemm_kernel(GemmP p)
     for (int a = 0; a < NF; a++)
 #pragma unroll
         for (int b = 0; b < MF; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+    const bool vec = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    // alpha = +-1 (every read-modify-write use on this path): start the accumulators from C so
+    // that the C reads overlap the operand pipeline instead of sitting in the epilogue
+    const bool preload = (p.beta != 0.0) && (p.alpha == 1.0 || p.alpha == -1.0);
+    if (preload) {
+        const double sc = p.beta * p.alpha;
+#pragma unroll
+        for (int a = 0; a < NF; a++) {
+            const int n = n0 + wn * WTN + a * 8 + fi;
+#pragma unroll
+            for (int b = 0; b < MF; b++) {
+                const int m = m0 + wm * WTM + b * 8 + 2 * fk;
+                if (n < p.N && m < p.M) {
+                    const double *cp = C + (long long)n * p.ldc + m;
+                    if (vec && m + 1 < p.M) {
+                        double2 o = __ldcs(reinterpret_cast<const double2 *>(cp));
+                        acc[a][b][0] = sc * o.x; acc[a][b][1] = sc * o.y;
+                    } else {
+                        acc[a][b][0] = sc * cp[0];
+                        if (m + 1 < p.M) acc[a][b][1] = sc * cp[1];
+                    }
+                }
+            }
+        }
+    }
 
     const int nk = (int)((kend - kbeg + KC - 1) / KC);
     // prologue
@@ -178,7 +203,7 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) dgemm_kernel(GemmP p)
     cp_wait<0>();
 
     // epilogue: thread owns C(m..m+1, n)
-    const bool vec = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    const double beta = preload ? 0.0 : p.beta;
 #pragma unroll
     for (int a = 0; a < NF; a++) {
         const int n = n0 + wn * WTN + a * 8 + fi;
@@ -191,17 +216,17 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) dgemm_kernel(GemmP p)
             double r0 = p.alpha * acc[a][b][0], r1 = p.alpha * acc[a][b][1];
             if (m + 1 < p.M) {
                 if (vec) {
-                    if (p.beta != 0.0) {
+                    if (beta != 0.0) {
                         double2 o = *reinterpret_cast<const double2 *>(cp);
-                        r0 = fma(p.beta, o.x, r0); r1 = fma(p.beta, o.y, r1);
+                        r0 = fma(beta, o.x, r0); r1 = fma(beta, o.y, r1);
                     }
                     *reinterpret_cast<double2 *>(cp) = make_double2(r0, r1);
                 } else {
-                    if (p.beta != 0.0) { r0 = fma(p.beta, cp[0], r0); r1 = fma(p.beta, cp[1], r1); }
+                    if (beta != 0.0) { r0 = fma(beta, cp[0], r0); r1 = fma(beta, cp[1], r1); }
                     cp[0] = r0; cp[1] = r1;
                 }
             } else {
-                if (p.beta != 0.0) r0 = fma(p.beta, cp[0], r0);
+                if (beta != 0.0) r0 = fma(beta, cp[0], r0);
                 cp[0] = r0;
             }
         }

@@ -744,6 +744,7 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
         }
         for (int k = m0 - 1; k >= k_stop; k--) {
             const int i = i_base + k, L = i;
+            if (c.debug_maxcols > 0 && (n - 1 - i) >= c.debug_maxcols) { ib = 0; break; }
             TrdP Q = P;
             Q.k = k; Q.L = L; Q.ndone = m0 - 1 - k; Q.first = 0;
             Q.has_next = (k - 1 >= k_stop) ? 1 : 0;

@@ -138,6 +138,8 @@ void eigenexa_b200_set_profiling(int level); /* 0 off, 1 async events (symv, syr
 /* per-launch symv_kernel milliseconds of the last eigen_trd (first entry = column n);
  * needs profiling >= 1; returns the number of launches recorded                        */
 int eigenexa_b200_symv_trace(float *out, int cap);
+/* profiling aid: eigen_trd stops after ncols columns (results are then meaningless); 0 = off */
+void eigenexa_b200_set_debug_maxcols(int ncols);
 const char *eigenexa_b200_last_error(void);
 
 #ifdef __cplusplus
