@@ -279,8 +279,8 @@ def launch_count(reset=False) -> int:
 
 
 def last_timings():
-    t = np.zeros(16)
-    lib().eigenexa_b200_last_timings(_dp(t), 16)
+    t = np.zeros(32)
+    lib().eigenexa_b200_last_timings(_dp(t), 32)
     return t
 
 

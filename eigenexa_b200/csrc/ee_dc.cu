@@ -21,6 +21,7 @@
 #include "ee_common.cuh"
 #include "ee_comm.h"
 #include <numeric>
+#include <chrono>
 
 namespace ee {
 
@@ -391,11 +392,18 @@ int dc_dev(int n, int nvec, const double *d_in, const double *e_in, double *w_ou
     std::vector<Rot> rots;
 
     double dc_flops = 0.0; long long n_defl_total = 0;
+    // breakdown (seconds): [16] leaves [17] z gather + host deflation [18] rotations + column gather
+    // [19] secular/Loewner/vectors [20] merge GEMMs + deflated copy [21] host sort
+    cudaEvent_t evs[5];
+    for (auto &e : evs) EE_CUDA(cudaEventCreate(&e));
+    double t_defl = 0, t_perm = 0, t_sec = 0, t_gemm = 0, t_sort = 0;
+    auto wall = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     // ---- merges (post-order) -----------------------------------------------------------------
     for (const Node &m : merges) {
         const int lo = m.lo, n1 = m.mid - m.lo, ns = m.hi - m.lo, n2 = ns - n1;
         double *Qb = Q + (long long)lo * ldq + lo, *Q2b = Q2 + (long long)lo * ldq + lo;
         double *Dn = D.data() + lo;
+        double tw0 = wall();
         gather_z_kernel<<<(ns + 255) / 256, 256, 0, st>>>(Q, ldq, lo, n1, ns, d_z);
         EE_CHECK_LAUNCH();
         EE_CUDA(cudaMemcpyAsync(hz.data(), d_z, sizeof(double) * ns, cudaMemcpyDeviceToHost, st));
@@ -465,7 +473,9 @@ int dc_dev(int n, int nvec, const double *d_in, const double *e_in, double *w_ou
         }
         for (int gidx = 0; gidx < k; gidx++) map[gidx] = grouped[gidx];
         for (size_t t = 0; t < defl.size(); t++) map[k + t] = defl[t];
+        t_defl += wall() - tw0;
         // ---- device: rotations, permuted copy, secular system, merge GEMMs ------------
+        EE_CUDA(cudaEventRecord(evs[0], st));
         if (!rots.empty()) {
             EE_CUDA(cudaMemcpyAsync(d_rot, rots.data(), sizeof(Rot) * rots.size(), cudaMemcpyHostToDevice, st));
             apply_rot_kernel<<<(ns + 127) / 128, 128, 0, st>>>(Qb, ldq, ns, d_rot, (int)rots.size());
@@ -478,6 +488,7 @@ int dc_dev(int n, int nvec, const double *d_in, const double *e_in, double *w_ou
             EE_CHECK_LAUNCH();
         }
         const long long ldv = ((long long)k + 1) & ~1LL;
+        EE_CUDA(cudaEventRecord(evs[1], st));
         EE_CUDA(cudaMemcpyAsync(d_dl, dl.data(), sizeof(double) * k, cudaMemcpyHostToDevice, st));
         EE_CUDA(cudaMemcpyAsync(d_w, ww.data(), sizeof(double) * k, cudaMemcpyHostToDevice, st));
         EE_CUDA(cudaMemcpyAsync(d_rowperm, rowperm.data(), sizeof(int) * k, cudaMemcpyHostToDevice, st));
@@ -489,6 +500,7 @@ int dc_dev(int n, int nvec, const double *d_in, const double *e_in, double *w_ou
         secvec_kernel<<<k, 256, 0, st>>>(k, d_dl, d_zt, d_tau, d_org, d_rowperm, Vs, ldv);
         EE_CHECK_LAUNCH();
         const int k12 = k1 + k2, k23 = k2 + k3;
+        EE_CUDA(cudaEventRecord(evs[2], st));
         n_defl_total += ns - k;
         dc_flops += 2.0 * (double)k * ((double)n1 * k12 + (double)n2 * k23);   // as mx_pdlaed1.F:291,304 counts them
         if (k12 > 0) dgemm_ex(st, 'N', 'N', n1, k, k12, 1.0, Q2b, ldq, Vs, ldv, 0.0, Qb, ldq, 1, 0);
@@ -498,7 +510,15 @@ int dc_dev(int n, int nvec, const double *d_in, const double *e_in, double *w_ou
         if (ns > k)
             EE_CUDA(cudaMemcpy2DAsync(Qb + (long long)k * ldq, ldq * sizeof(double), Q2b + (long long)k * ldq, ldq * sizeof(double),
                                       (size_t)ns * sizeof(double), ns - k, cudaMemcpyDeviceToDevice, st));
+        EE_CUDA(cudaEventRecord(evs[3], st));
         EE_CUDA(cudaStreamSynchronize(st));
+        {
+            float ms;
+            cudaEventElapsedTime(&ms, evs[0], evs[1]); t_perm += ms * 1e-3;
+            cudaEventElapsedTime(&ms, evs[1], evs[2]); t_sec += ms * 1e-3;
+            cudaEventElapsedTime(&ms, evs[2], evs[3]); t_gemm += ms * 1e-3;
+        }
+        double tw1 = wall();
         // ---- new physical eigenvalues and their ascending order -----------------------
         {
             std::vector<double> tmp(ns);
@@ -509,7 +529,10 @@ int dc_dev(int n, int nvec, const double *d_in, const double *e_in, double *w_ou
             std::stable_sort(neword.begin(), neword.begin() + ns, [&](int a, int b) { return Dn[a] < Dn[b]; });
             for (int j = 0; j < ns; j++) ord[lo + j] = neword[j];
         }
+        t_sort += wall() - tw1;
     }
+    for (auto &e : evs) cudaEventDestroy(e);
+    c.timings[17] = t_defl; c.timings[18] = t_perm; c.timings[19] = t_sec; c.timings[20] = t_gemm; c.timings[21] = t_sort;
     // ---- outputs: w ascending, z = local cyclic part of Q(:, ord) ---------------------------------
     {
         std::vector<double> wv(n);

@@ -18,8 +18,10 @@ namespace ee {
 
 namespace {
 
-constexpr int MB_MAX = 128;
+constexpr int MB_MAX = 256;   // nsm of the reference (src/eigen_devel.F:88-91)
+constexpr int TB = 128;       // diagonal block handled by one tinv CTA
 constexpr int KSPLIT = 64;
+constexpr int SS_SPLIT_MAX = 6;
 
 // V(g, c) = u_{i0+c}(g) for g < i0+c, from the local cyclic pieces of a (zero elsewhere)
 __global__ void gather_v_kernel(const double *A, int lda, int px, int py, int x, int y, int i0, int mb, int rows,
@@ -43,37 +45,71 @@ __global__ void pick_rows_kernel(const double *V, int ldv, int px, int x, int nr
     Vx[(size_t)c * ldvx + jl] = (jl < nrl) ? V[(size_t)c * ldv + (size_t)jl * px + x] : 0.0;
 }
 
-// T = S^{-1},  S = -(sum of split-K partials of V^T V) lower, diagonal halved (0 -> 1).
-// One CTA; thread j solves S x = e_j by forward substitution (column j of T).
-__global__ void __launch_bounds__(MB_MAX) tinv_kernel(const double *SMpart, int nsplit, int mb, double *T)
+// S = -(sum of split-K partials of V^T V), diagonal halved, 0 -> 1 (trbakwy4_body.F:206-213,302-313)
+__global__ void reduce_s_kernel(const double *SMpart, int nsplit, int mb, double *S, double *T)
 {
-    extern __shared__ double S[];  // mb x (mb+1) row-major-ish: S[i*(mb+1)+k]
-    const int ld = mb + 1;
-    for (int idx = threadIdx.x; idx < mb * mb; idx += blockDim.x) {
-        int i = idx % mb, k = idx / mb;  // column-major partials: (i,k) at i + k*mb
-        double s = 0.0;
-        for (int z = 0; z < nsplit; z++) s += SMpart[(size_t)z * mb * mb + idx];
-        s = -s;
-        if (i == k) s = (s == 0.0) ? 1.0 : 0.5 * s;
-        S[i * ld + k] = s;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= mb * mb) return;
+    const int i = idx % mb, k = idx / mb;
+    double s = 0.0;
+    for (int z = 0; z < nsplit; z++) s += SMpart[(size_t)z * mb * mb + idx];
+    s = -s;
+    if (i == k) s = (s == 0.0) ? 1.0 : 0.5 * s;
+    S[idx] = s;
+    T[idx] = 0.0;
+}
+
+// T_bb = S_bb^{-1} for the diagonal blocks (<= 128) of the lower triangular S; one CTA per block,
+// thread j solves S x = e_j by forward substitution (column j of the block).
+__global__ void __launch_bounds__(TB) tinv_kernel(const double *S, int lds, int mb, double *T)
+{
+    extern __shared__ double Sb[];  // bs x (bs+1)
+    const int off = blockIdx.x * TB;
+    const int bs = min(TB, mb - off);
+    const int ld = bs + 1;
+    for (int idx = threadIdx.x; idx < bs * bs; idx += blockDim.x) {
+        int i = idx % bs, k = idx / bs;
+        Sb[i * ld + k] = S[(size_t)(off + k) * lds + off + i];
     }
     __syncthreads();
     const int j = threadIdx.x;
-    if (j < mb) {
-        // x lives in column j of T (global memory, L1/L2 resident)
-        for (int i = 0; i < j; i++) T[(size_t)j * mb + i] = 0.0;
-        T[(size_t)j * mb + j] = 1.0 / S[j * ld + j];
-        for (int i = j + 1; i < mb; i++) {
+    if (j < bs) {
+        double *tc = T + (size_t)(off + j) * lds + off;  // column j of the block, L1/L2 resident
+        tc[j] = 1.0 / Sb[j * ld + j];
+        for (int i = j + 1; i < bs; i++) {
             double s0 = 0.0, s1 = 0.0;
             int k = j;
             for (; k + 1 < i; k += 2) {
-                s0 = fma(S[i * ld + k], T[(size_t)j * mb + k], s0);
-                s1 = fma(S[i * ld + k + 1], T[(size_t)j * mb + k + 1], s1);
+                s0 = fma(Sb[i * ld + k], tc[k], s0);
+                s1 = fma(Sb[i * ld + k + 1], tc[k + 1], s1);
             }
-            if (k < i) s0 = fma(S[i * ld + k], T[(size_t)j * mb + k], s0);
-            T[(size_t)j * mb + i] = -(s0 + s1) / S[i * ld + i];
+            if (k < i) s0 = fma(Sb[i * ld + k], tc[k], s0);
+            tc[i] = -(s0 + s1) / Sb[i * ld + i];
         }
     }
+}
+
+// out = sum_z part[z]  (fixed order)
+__global__ void reduce_parts_kernel(const double *part, long long stride, int nsplit, long long count, double *out)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        double s = part[i];
+        for (int z = 1; z < nsplit; z++) s += part[(long long)z * stride + i];
+        out[i] = s;
+    }
+}
+
+// split-K factor that fills the last wave of a deep-K GEMM (tiles x s work items over `slots`)
+int choose_ksplit(long long tiles, int K, int slots)
+{
+    int best = 1; double beste = 0.0;
+    for (int s = 1; s <= SS_SPLIT_MAX; s++) {
+        if (s > 1 && K / s < 2048) break;
+        double w = (double)tiles * s / slots;
+        double e = w / ceil(w);
+        if (e > beste + 0.02) { beste = e; best = s; }
+    }
+    return best;
 }
 
 }  // namespace
@@ -85,7 +121,10 @@ void trbak_dev(int n, int nvec, const double *a, int lda, double *z, int ldz, co
     const Grid &g = c.g;
     cudaStream_t st = c.stream;
     if (n <= 1 || nvec <= 0) return;
+    // m_backward is a blocking hint (reference default 128, cap nsm = 256).  The two GEMMs per
+    // block run at K = mb resp. M = mb; wide blocks keep the C read-modify-write of Z hidden.
     int mb = m_backward < MB_MAX ? m_backward : MB_MAX;
+    if (n >= 8192 && mb < MB_MAX) mb = MB_MAX;
     if (mb < 1) mb = 1;
     if (mb > n - 1) mb = n - 1;
     const int nvl = cyc_count(nvec, g.py, g.y);
@@ -96,11 +135,15 @@ void trbak_dev(int n, int nvec, const double *a, int lda, double *z, int ldz, co
     double *V = (double *)dev_alloc((size_t)ldv * mb * sizeof(double));
     double *Vx = (g.px > 1) ? (double *)dev_alloc((size_t)ldvx * mb * sizeof(double)) : V;
     double *SMp = (double *)dev_alloc((size_t)KSPLIT * mb * mb * sizeof(double));
+    double *S = (double *)dev_alloc((size_t)mb * mb * sizeof(double));
     double *T = (double *)dev_alloc((size_t)mb * mb * sizeof(double));
-    const int ldss = mb;
-    double *SS = (double *)dev_alloc((size_t)ldss * (nvl > 0 ? nvl : 1) * sizeof(double));
-    double *SS2 = (double *)dev_alloc((size_t)ldss * (nvl > 0 ? nvl : 1) * sizeof(double));
-    EE_CUDA(cudaFuncSetAttribute(tinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MB_MAX * (MB_MAX + 1) * sizeof(double))));
+    double *Wt = (double *)dev_alloc((size_t)mb * mb * sizeof(double));
+    const int ldss = (mb + 1) & ~1;
+    const size_t ss_elems = (size_t)ldss * (nvl > 0 ? nvl : 1);
+    double *SSp = (double *)dev_alloc(ss_elems * SS_SPLIT_MAX * sizeof(double));
+    double *SS = (double *)dev_alloc(ss_elems * sizeof(double));
+    double *SS2 = (double *)dev_alloc(ss_elems * sizeof(double));
+    EE_CUDA(cudaFuncSetAttribute(tinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TB * (TB + 1) * sizeof(double))));
 
     // reflector columns i = 1..n-1 ; first block takes the remainder (trbakwy4.F:292)
     int i0 = 1;
@@ -125,12 +168,30 @@ void trbak_dev(int n, int nvec, const double *a, int lda, double *z, int ldz, co
         // ---- S = -V^T V from the replicated panel (split-K partials), T = S^{-1} (K12,K13) ---
         int ks = rows / 512; if (ks < 1) ks = 1; if (ks > KSPLIT) ks = KSPLIT;
         dgemm_ex(st, 'T', 'N', cur, cur, rows, 1.0, V, ldv, V, ldv, 0.0, SMp, cur, ks, (long long)cur * cur);
-        tinv_kernel<<<1, MB_MAX, (size_t)cur * (cur + 1) * sizeof(double), st>>>(SMp, ks, cur, T);
+        reduce_s_kernel<<<(cur * cur + 255) / 256, 256, 0, st>>>(SMp, ks, cur, S, T);
         EE_CHECK_LAUNCH();
+        const int nb = (cur + TB - 1) / TB;
+        const int bs0 = cur < TB ? cur : TB;
+        tinv_kernel<<<nb, TB, (size_t)bs0 * (bs0 + 1) * sizeof(double), st>>>(S, cur, cur, T);
+        EE_CHECK_LAUNCH();
+        if (nb == 2) {
+            // T21 = -T22 S21 T11
+            const int b1 = TB, b2 = cur - TB;
+            dgemm(st, 'N', 'N', b2, b1, b1, 1.0, S + b1, cur, T, cur, 0.0, Wt, b2);
+            dgemm(st, 'N', 'N', b2, b1, b2, -1.0, T + (size_t)b1 * cur + b1, cur, Wt, b2, 0.0, T + b1, cur);
+        }
         if (nvl > 0) {
-            // ---- SS = Vx^T Z  (K12) ; sum over the x group (C13) ---------------------------
-            if (nrl > 0) dgemm(st, 'T', 'N', cur, nvl, nrl, 1.0, Vx, ldx, z, ldz, 0.0, SS, ldss);
-            else EE_CUDA(cudaMemsetAsync(SS, 0, (size_t)ldss * nvl * sizeof(double), st));
+            // ---- SS = Vx^T Z  (K12), split-K sized to fill the last wave ; x-group sum (C13) -----
+            if (nrl > 0) {
+                const long long tiles = (long long)((cur + 127) / 128) * ((nvl + 127) / 128);
+                const int sk = choose_ksplit(tiles, nrl, c.sm_count);
+                if (sk == 1) dgemm(st, 'T', 'N', cur, nvl, nrl, 1.0, Vx, ldx, z, ldz, 0.0, SS, ldss);
+                else {
+                    dgemm_ex(st, 'T', 'N', cur, nvl, nrl, 1.0, Vx, ldx, z, ldz, 0.0, SSp, ldss, sk, (long long)ss_elems);
+                    reduce_parts_kernel<<<c.sm_count * 4, 256, 0, st>>>(SSp, (long long)ss_elems, sk, (long long)ldss * nvl, SS);
+                    EE_CHECK_LAUNCH();
+                }
+            } else EE_CUDA(cudaMemsetAsync(SS, 0, (size_t)ldss * nvl * sizeof(double), st));
             if (g.px > 1) comm_allreduce_sum(SS, (size_t)ldss * nvl, COMM_X, st);
             // ---- SS2 = T SS ; Z += Vx SS2  (K14) ---------------------------------------------
             dgemm(st, 'N', 'N', cur, nvl, cur, 1.0, T, cur, SS, ldss, 0.0, SS2, ldss);
@@ -140,7 +201,7 @@ void trbak_dev(int n, int nvec, const double *a, int lda, double *z, int ldz, co
     }
     EE_CUDA(cudaStreamSynchronize(st));
     dev_free(V); if (g.px > 1) dev_free(Vx);
-    dev_free(SMp); dev_free(T); dev_free(SS); dev_free(SS2);
+    dev_free(SMp); dev_free(S); dev_free(T); dev_free(Wt); dev_free(SSp); dev_free(SS); dev_free(SS2);
 }
 
 }  // namespace ee

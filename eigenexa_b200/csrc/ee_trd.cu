@@ -31,7 +31,7 @@ namespace {
 
 constexpr int TR = 128;     // tile rows (local)
 constexpr int TC = 64;      // tile cols (local)
-constexpr int SW = 4;       // sub-tiles swept per CTA along a row strip
+constexpr int SW = 4;       // max sub-tiles swept per CTA along a row strip (TrdP::sw <= SW)
 constexpr int NCH = 32;     // row chunks for the panel dot products
 constexpr int MAXM = 256;   // max panel width
 
@@ -42,6 +42,7 @@ struct TrdP {
     int L;                              // reflector length = global column index i (0-based)
     int k, m0, ndone;                   // slot in panel, panel width, finished pairs (slots k+1..m0-1)
     int i_base;
+    int sw;                             // sub-tiles per strip for this launch (1, 2 or 4)
     double *U, *V, *W;                  // replicated panels, npad x m
     double *ucur, *unext;               // current / next raw column (length npad)
     double *Prow, *Pcol; int ldprow, ldpcol;
@@ -69,10 +70,10 @@ __device__ __forceinline__ int ntile_rows(const TrdP &P, int t, int nclL)
     if (cmax_g <= P.x) return 0;
     return (int)((cmax_g - P.x - 1) / ((long long)TR * P.px)) + 1;
 }
-__device__ __forceinline__ int nstrips_of(int nclL) { return (nclL + SW * TC - 1) / (SW * TC); }
+__device__ __forceinline__ int nstrips_of(const TrdP &P, int nclL) { return (nclL + P.sw * TC - 1) / (P.sw * TC); }
 __device__ __forceinline__ int strip_rows(const TrdP &P, int sc, int nclL)
 {
-    int tlast = min((sc + 1) * SW, (nclL + TC - 1) / TC) - 1;
+    int tlast = min((sc + 1) * P.sw, (nclL + TC - 1) / TC) - 1;
     return ntile_rows(P, tlast, nclL);
 }
 
@@ -118,8 +119,8 @@ __device__ __forceinline__ void symv_strip(const TrdP &P, int br, int sc, int nc
         acc_row[q] = 0.0;
     }
     const long long rmax_g = (long long)(r0 + TR - 1) * P.px + P.x;
-    for (int st = 0; st < SW; st++) {
-        const int t = sc * SW + st;
+    for (int st = 0; st < P.sw; st++) {
+        const int t = sc * P.sw + st;
         const int c0 = t * TC;
         if (c0 >= nclL) break;
         if (br >= ntile_rows(P, t, nclL)) continue;
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(256, 2) symv_kernel(TrdP P, int gx, int ntile_
         return;
     }
     const int nclL = ncl_of(P);
-    const int nsc = nstrips_of(nclL);
+    const int nsc = nstrips_of(P, nclL);
     const int bx = bid % gx, by = bid / gx;
     // fold the triangle: pair strip (nsc-1-bx) with strip bx
     const int sc1 = nsc - 1 - bx, sc2 = bx;
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(VR * VS) pvec_kernel(TrdP P)
     __shared__ unsigned int s_last;
     const int nd = P.ndone;
     const int nclL = ncl_of(P);
-    const int nsc = nstrips_of(nclL);
+    const int nsc = nstrips_of(P, nclL);
     if (MODE != 2) {
         for (int s = threadIdx.x; s < nsc; s += blockDim.x) s_nbr[s] = strip_rows(P, s, nclL);
     }
@@ -638,6 +639,12 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
     int m = m_forward < n ? m_forward : n;
     if (m < 1) m = 1;
     if (m > MAXM) m = MAXM;
+    // m_forward is the reference's blocking hint (default 48).  The trailing update is one
+    // GEMM with K = 2*width; at K = 96 its C read-modify-write (16 B per 4*width flop) is not
+    // hidden, so wide trailing matrices use a wider internal panel (same T up to rounding).
+    // The panel-internal vector work grows with the width, hence only above WIDE_L.
+    constexpr int WIDE_W = 128, WIDE_L = 16384;
+    const int mmax = (n > WIDE_L && m < WIDE_W) ? WIDE_W : m;
 
     // ---- internal padded copy of the local matrix ------------------------------------
     const int lda = trd_lda_pad(nrl), nclp = trd_ncl_pad(ncl);
@@ -654,17 +661,17 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
 
     // ---- workspace ---------------------------------------------------------------------
     const int npad = round_up(n + 1, 256);
-    const int nstrip_max = (nclp + SW * TC - 1) / (SW * TC);
+    const int nstrip_max = (nclp + TC - 1) / TC;   // strips of one tile (sw = 1) need the most rows
     const int nbr_max = lda / TR;
     const int maxvb = (n + VR) / VR + 2;
     size_t wsz = 0;
     auto take = [&](size_t cnt) { size_t o = wsz; wsz += (cnt + 31) & ~(size_t)31; return o; };
-    size_t oU = take((size_t)npad * m), oV = take((size_t)npad * m), oW = take((size_t)npad * m);
+    size_t oU = take((size_t)npad * mmax), oV = take((size_t)npad * mmax), oW = take((size_t)npad * mmax);
     size_t oU1 = take(npad), oU2 = take(npad), oP = take(npad);
     size_t oProw = take((size_t)nstrip_max * lda), oPcol = take((size_t)nbr_max * nclp);
     size_t oDots = take((size_t)NCH * 2 * MAXM), oSt = take(2 * MAXM), oPart = take(2 * (size_t)maxvb);
     size_t oScal = take(32), oTick = take(32);
-    size_t oUVx = take((size_t)lda * 2 * m), oVUy = take((size_t)nclp * 2 * m);
+    size_t oUVx = take((size_t)lda * 2 * mmax), oVUy = take((size_t)nclp * 2 * mmax);
     double *ws = (double *)dev_alloc(wsz * sizeof(double));
     EE_CUDA(cudaMemsetAsync(ws, 0, wsz * sizeof(double), st));
 
@@ -715,19 +722,22 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
     if (c.profiling >= 2) EE_CUDA(cudaStreamSynchronize(st));
     double tw1 = wall();
 
-    const int nblk = (n - 1) / m + 1;
-    for (int ib = nblk; ib >= 1; ib--) {
-        const int i_base = (ib - 1) * m;
-        const int m0 = (m < n - i_base) ? m : n - i_base;
+    // panels from the right; boundaries at multiples of m (as the reference) while the
+    // narrow width is in use, free-running for the wide panels
+    int col_end = n;
+    while (col_end > 2) {
+        int i_base;
+        if (col_end > WIDE_L && mmax > m) i_base = col_end - mmax;
+        else i_base = ((col_end - 1) / m) * m;
+        if (i_base < 0) i_base = 0;
+        const int m0 = col_end - i_base;
+        const int ib = (i_base > 0) ? 2 : 1;   // ib > 1 <=> a trailing matrix remains
         const int k_stop = (i_base == 0) ? 2 : 0;
-        if (i_base + m0 - 1 < 2) {
-            // nothing to reflect (n == 2): fall through to the final step
-            break;
-        }
+        col_end = i_base;
         P.i_base = i_base; P.m0 = m0;
         // panel load (+ zero U,V)
         {
-            dim3 grid((npad + 255) / 256, m);
+            dim3 grid((npad + 255) / 256, m0);
             TrdP Q = P;
             panel_load_kernel<<<grid, 256, 0, st>>>(Q, 1);
             EE_CHECK_LAUNCH();
@@ -744,18 +754,22 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
         }
         for (int k = m0 - 1; k >= k_stop; k--) {
             const int i = i_base + k, L = i;
-            if (c.debug_maxcols > 0 && (n - 1 - i) >= c.debug_maxcols) { ib = 0; break; }
+            if (c.debug_maxcols > 0 && (n - 1 - i) >= c.debug_maxcols) { col_end = 0; break; }
             TrdP Q = P;
             Q.k = k; Q.L = L; Q.ndone = m0 - 1 - k; Q.first = 0;
             Q.has_next = (k - 1 >= k_stop) ? 1 : 0;
             // ---- SYMV --------------------------------------------------------------
             const int nclL = cyc_count(L, g.py, g.y);
-            const int nsc = (nclL + SW * TC - 1) / (SW * TC);
+            // long strips amortise the row-sum reduction at large L; short ones give the
+            // latency-bound small trailing matrices more CTAs
+            const int sw = (L > 12288) ? 4 : (L > 6144) ? 2 : 1;
+            Q.sw = sw;
+            const int nsc = (nclL + sw * TC - 1) / (sw * TC);
             int gx = (nsc + 1) / 2, gy = 0;
             if (nsc > 0) {
                 // rows of the biggest strip + rows of the smallest
                 auto strip_rows_h = [&](int sc) {
-                    int tlast = std::min((sc + 1) * SW, (nclL + TC - 1) / TC) - 1;
+                    int tlast = std::min((sc + 1) * sw, (nclL + TC - 1) / TC) - 1;
                     int clast = std::min((tlast + 1) * TC, nclL) - 1;
                     if (clast < tlast * TC) return 0;
                     long long cmax_g = (long long)clast * g.py + g.y;
@@ -809,12 +823,12 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
             if (nrl_b > 0 && ncl_b > 0) {
                 TrdP Q = P;
                 int mx = nrl_b > ncl_b ? nrl_b : ncl_b;
-                dim3 grid((mx + 255) / 256, 2 * m);
-                pack_uv_kernel<<<grid, 256, 0, st>>>(Q, UVx, lda, nrl_b, VUy, nclp, ncl_b, m);
+                dim3 grid((mx + 255) / 256, 2 * m0);
+                pack_uv_kernel<<<grid, 256, 0, st>>>(Q, UVx, lda, nrl_b, VUy, nclp, ncl_b, m0);
                 EE_CHECK_LAUNCH();
                 TriSpec tri; tri.mode = 1; tri.px = g.px; tri.py = g.py; tri.x = g.x; tri.y = g.y;
                 prof_begin(2);
-                dgemm(st, 'N', 'T', nrl_b, ncl_b, 2 * m, -1.0, UVx, lda, VUy, nclp, 1.0, A, lda, tri);
+                dgemm(st, 'N', 'T', nrl_b, ncl_b, 2 * m0, -1.0, UVx, lda, VUy, nclp, 1.0, A, lda, tri);
                 prof_end(t_syr2k, 2);
             }
         }

@@ -21,6 +21,7 @@ for n in [int(v) for v in sys.argv[1:]]:
     tm = E.last_timings()
     flops = 4.0 / 3.0 * n**3 + 2.0 * n**3
     r = {"n": n, "wall_s": t1, "trd_s": tm[1], "dc_s": tm[2], "trbak_s": tm[3], "tflops(trd+bak)": flops / t1 / 1e12,
+         "dc_flops": tm[13], "dc_deflated": tm[14], "dc_defl_s": tm[17], "dc_perm_s": tm[18], "dc_sec_s": tm[19], "dc_gemm_s": tm[20], "dc_sort_s": tm[21],
          "launches": E.launch_count(True), "mem_peak_GB": torch.cuda.max_memory_allocated() / 1e9}
     print(json.dumps(r)); sys.stdout.flush()
     del a
