@@ -198,7 +198,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(lib_stream)
     t0 = time.perf_counter()
-    stage = np.zeros(16)
+    stage = np.zeros(32)
     for _ in range(args.steps):
         step_dev()
         stage += E.last_timings()

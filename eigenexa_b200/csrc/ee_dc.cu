@@ -28,6 +28,7 @@ namespace ee {
 namespace {
 
 constexpr int LEAF = 32;
+constexpr int DIST_MIN = 1024;   // merges at least this large are split over the ranks
 constexpr double EPS = 2.220446049250313e-16;  // 2^-52
 constexpr double HALF_EPS = 1.1102230246251565e-16;
 
@@ -364,6 +365,13 @@ int dc_dev(int n, int nvec, const double *d_in, const double *e_in, double *w_ou
     double *Q = (double *)dev_alloc(qbytes);
     double *Q2 = merges.empty() ? nullptr : (double *)dev_alloc(qbytes);
     double *Vs = merges.empty() ? nullptr : (double *)dev_alloc(qbytes);
+    // multi-rank merge buffers: this rank's column slice and the gathered block
+    double *Tb = nullptr, *Gb = nullptr;
+    if (g.nnod > 1 && n >= DIST_MIN) {
+        const size_t sl = (size_t)(((n + g.nnod - 1) / g.nnod + 2) & ~1);
+        Tb = (double *)dev_alloc((size_t)(n + 2) * sl * sizeof(double));
+        Gb = (double *)dev_alloc((size_t)(n + 2) * sl * g.nnod * sizeof(double));
+    }
     EE_CUDA(cudaMemsetAsync(Q, 0, qbytes, st));
     // small device arrays
     double *dd = (double *)dev_alloc(sizeof(double) * n * 8);
@@ -503,10 +511,30 @@ int dc_dev(int n, int nvec, const double *d_in, const double *e_in, double *w_ou
         EE_CUDA(cudaEventRecord(evs[2], st));
         n_defl_total += ns - k;
         dc_flops += 2.0 * (double)k * ((double)n1 * k12 + (double)n2 * k23);   // as mx_pdlaed1.F:291,304 counts them
+        if (g.nnod > 1 && ns >= DIST_MIN && k >= 2 * g.nnod) {
+            // multi-rank: every rank forms its slice of the k merged columns, then one
+            // all-gather puts the whole block on every rank (everything else is replicated, so
+            // all ranks take identical deflation decisions in the next level)
+            const int P = g.nnod;
+            int slice = ((k + P - 1) / P + 1) & ~1;
+            const long long ldt = ((long long)ns + 1) & ~1LL;
+            const int c0 = std::min(k, g.inod * slice), c1 = std::min(k, c0 + slice);
+            const int wdt = c1 - c0;
+            if (wdt > 0) {
+                if (k12 > 0) dgemm_ex(st, 'N', 'N', n1, wdt, k12, 1.0, Q2b, ldq, Vs + (long long)c0 * ldv, ldv, 0.0, Tb, ldt, 1, 0);
+                else EE_CUDA(cudaMemset2DAsync(Tb, ldt * sizeof(double), 0, (size_t)n1 * sizeof(double), wdt, st));
+                if (k23 > 0) dgemm_ex(st, 'N', 'N', n2, wdt, k23, 1.0, Q2b + n1 + (long long)k1 * ldq, ldq, Vs + k1 + (long long)c0 * ldv, ldv, 0.0, Tb + n1, ldt, 1, 0);
+                else EE_CUDA(cudaMemset2DAsync(Tb + n1, ldt * sizeof(double), 0, (size_t)n2 * sizeof(double), wdt, st));
+            }
+            comm_allgather(Tb, Gb, (size_t)ldt * slice, COMM_WORLD, st);
+            EE_CUDA(cudaMemcpy2DAsync(Qb, ldq * sizeof(double), Gb, ldt * sizeof(double), (size_t)ns * sizeof(double), k,
+                                      cudaMemcpyDeviceToDevice, st));
+        } else {
         if (k12 > 0) dgemm_ex(st, 'N', 'N', n1, k, k12, 1.0, Q2b, ldq, Vs, ldv, 0.0, Qb, ldq, 1, 0);
         else EE_CUDA(cudaMemset2DAsync(Qb, ldq * sizeof(double), 0, (size_t)n1 * sizeof(double), k, st));
         if (k23 > 0) dgemm_ex(st, 'N', 'N', n2, k, k23, 1.0, Q2b + n1 + (long long)k1 * ldq, ldq, Vs + k1, ldv, 0.0, Qb + n1, ldq, 1, 0);
         else EE_CUDA(cudaMemset2DAsync(Qb + n1, ldq * sizeof(double), 0, (size_t)n2 * sizeof(double), k, st));
+        }
         if (ns > k)
             EE_CUDA(cudaMemcpy2DAsync(Qb + (long long)k * ldq, ldq * sizeof(double), Q2b + (long long)k * ldq, ldq * sizeof(double),
                                       (size_t)ns * sizeof(double), ns - k, cudaMemcpyDeviceToDevice, st));
@@ -548,6 +576,8 @@ int dc_dev(int n, int nvec, const double *d_in, const double *e_in, double *w_ou
     }
     c.timings[13] = dc_flops; c.timings[14] = (double)n_defl_total;
     dev_free(Q); if (Q2) dev_free(Q2); if (Vs) dev_free(Vs);
+    if (Tb) dev_free(Tb);
+    if (Gb) dev_free(Gb);
     dev_free(dd); dev_free(di); dev_free(d_rot); dev_free(d_leaves);
     return 0;
 }

@@ -15,7 +15,7 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("nproc,n,mtype,mode", [(2, 600, 2, "A"), (2, 257, 0, "A"), (2, 500, 2, "N"), (4, 700, 2, "A"),
+@pytest.mark.parametrize("nproc,n,mtype,mode", [(2, 600, 2, "A"), (2, 257, 0, "A"), (2, 500, 2, "N"), (2, 1300, 2, "A"), (4, 700, 2, "A"), (4, 1500, 0, "A"),
                                                 (8, 900, 2, "A")])
 def test_eigen_s_multi_rank(nproc, n, mtype, mode):
     if _ngpu() < nproc:

@@ -11,6 +11,7 @@ from oracle import oracle as O
 
 n = int(sys.argv[1]); mtype = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 mode = sys.argv[3] if len(sys.argv) > 3 else "A"
+check = (len(sys.argv) <= 4) or sys.argv[4] != "nocheck"
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
@@ -23,6 +24,12 @@ w = np.zeros(n); z = np.zeros((nx, ny), order="F")
 dist.barrier(); t0 = time.perf_counter()
 E.eigen_s(n, a, w, z, mode=mode)
 dist.barrier(); t1 = time.perf_counter() - t0
+tm = E.last_timings()
+if not check:
+    if rank == 0:
+        print(json.dumps({"n": n, "grid": f"{px}x{py}", "mode": mode, "seconds": t1, "h2d": tm[0], "trd": tm[1], "dc": tm[2],
+                          "trbak": tm[3], "d2h": tm[4], "dc_gemm": tm[20], "dc_sec": tm[19]}), flush=True)
+    E.eigen_free(); dist.destroy_process_group(); sys.exit(0)
 parts = [None] * world if rank == 0 else None
 nr, nc = E.eigen_loop_end(n, px, xi), E.eigen_loop_end(n, py, yi)
 dist.gather_object(((xi, yi), z[:nr, :nc].copy(), w.copy()), parts, dst=0)
@@ -31,7 +38,7 @@ if rank == 0:
     assert all(np.array_equal(ws[0], v) for v in ws), "w differs between ranks"
     full = O.sym_from_upper(O.mat_set(n, mtype))
     wl = np.linalg.eigvalsh(full)
-    out = {"n": n, "grid": f"{px}x{py}", "mode": mode, "seconds": t1,
+    out = {"n": n, "grid": f"{px}x{py}", "mode": mode, "seconds": t1, "trd": tm[1], "dc": tm[2], "trbak": tm[3],
            "w_err_over_tol": float(np.abs(w - wl).max() / (10 * n * O.EPS * np.linalg.norm(full)))}
     if mode != "N":
         Z = O.gather_cyclic({p[0]: p[1] for p in parts}, n, n, px, py)
