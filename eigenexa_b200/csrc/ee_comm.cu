@@ -75,6 +75,13 @@ struct Comm {
     ncclComm_t c[3] = {nullptr, nullptr, nullptr};
     int size[3] = {1, 1, 1};
     int rank[3] = {0, 0, 0};
+    // peer ring
+    bool peer_tried = false, peer_ok = false;
+    size_t peer_slot = 0;
+    void *peer_local = nullptr;
+    void *peer_ptr[PEER_MAX] = {nullptr};
+    unsigned long long epoch = 0;
+    int *peer_err = nullptr;
 };
 
 int comm_get_unique_id(unsigned char *id128)
@@ -106,10 +113,95 @@ int comm_init(const unsigned char *unique_id, int rank, int nranks, const Grid &
     return 0;
 }
 
+static void peer_release(Comm *cm_)
+{
+    if (!cm_->peer_local) return;
+    for (int q = 0; q < cm_->size[COMM_WORLD]; q++)
+        if (q != cm_->rank[COMM_WORLD] && cm_->peer_ptr[q]) cudaIpcCloseMemHandle(cm_->peer_ptr[q]);
+    cudaFree(cm_->peer_local);
+    if (cm_->peer_err) cudaFree(cm_->peer_err);
+    cm_->peer_local = nullptr; cm_->peer_err = nullptr; cm_->peer_ok = false; cm_->peer_slot = 0;
+}
+
+bool comm_peer_setup(size_t slot_doubles, PeerView *view)
+{
+    Comm *m = ctx().comm;
+    if (!m || m->size[COMM_WORLD] <= 1 || m->size[COMM_WORLD] > PEER_MAX) return false;
+    const char *off = getenv("EIGENEXA_B200_NO_PEER");
+    if (off && off[0] == '1') return false;
+    const int P = m->size[COMM_WORLD], r = m->rank[COMM_WORLD];
+    cudaStream_t st = ctx().stream;
+    if (m->peer_tried && !m->peer_ok && m->peer_slot >= slot_doubles) return false;
+    if (!m->peer_ok || m->peer_slot < slot_doubles) {
+        // (re)build: collective over all ranks (every rank sees the same sizes)
+        EE_CUDA(cudaStreamSynchronize(st));
+        comm_barrier(st);
+        peer_release(m);
+        m->peer_tried = true;
+        m->peer_slot = slot_doubles;
+        const size_t bytes = (size_t)2 * P * slot_doubles * sizeof(double) + 2 * PEER_MAX * sizeof(unsigned long long);
+        if (cudaMalloc(&m->peer_local, bytes) != cudaSuccess) { cudaGetLastError(); m->peer_local = nullptr; }
+        int okl = m->peer_local != nullptr;
+        cudaIpcMemHandle_t h;
+        memset(&h, 0, sizeof h);
+        if (okl && cudaIpcGetMemHandle(&h, m->peer_local) != cudaSuccess) { cudaGetLastError(); okl = 0; }
+        if (okl) EE_CUDA(cudaMemsetAsync(m->peer_local, 0, bytes, st));
+        EE_CUDA(cudaMalloc((void **)&m->peer_err, sizeof(int)));
+        EE_CUDA(cudaMemsetAsync(m->peer_err, 0, sizeof(int), st));
+        // exchange (ok flag + 64-byte handle) through NCCL as raw bytes
+        const size_t rec = 8 + sizeof(cudaIpcMemHandle_t);
+        unsigned char *d_all = (unsigned char *)dev_alloc(rec * P);
+        std::vector<unsigned char> h_all(rec * P, 0);
+        long long okll = okl;
+        memcpy(h_all.data() + rec * r, &okll, 8);
+        memcpy(h_all.data() + rec * r + 8, &h, sizeof h);
+        EE_CUDA(cudaMemcpyAsync(d_all + rec * r, h_all.data() + rec * r, rec, cudaMemcpyHostToDevice, st));
+        EE_NCCL(g_nccl.AllGather(d_all + rec * r, d_all, rec, /*ncclChar*/ 0, m->c[COMM_WORLD], st));
+        EE_CUDA(cudaMemcpyAsync(h_all.data(), d_all, rec * P, cudaMemcpyDeviceToHost, st));
+        EE_CUDA(cudaStreamSynchronize(st));
+        dev_free(d_all);
+        bool all_ok = true;
+        for (int q = 0; q < P; q++) { long long v; memcpy(&v, h_all.data() + rec * q, 8); all_ok = all_ok && v == 1; }
+        int opened = 1;
+        if (all_ok) {
+            for (int q = 0; q < P; q++) {
+                if (q == r) { m->peer_ptr[q] = m->peer_local; continue; }
+                cudaIpcMemHandle_t hq;
+                memcpy(&hq, h_all.data() + rec * q + 8, sizeof hq);
+                if (cudaIpcOpenMemHandle(&m->peer_ptr[q], hq, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    cudaGetLastError(); m->peer_ptr[q] = nullptr; opened = 0;
+                }
+            }
+        } else opened = 0;
+        // everyone must agree
+        double *d_ok = (double *)dev_alloc(sizeof(double));
+        double hv = opened ? 0.0 : 1.0;
+        EE_CUDA(cudaMemcpyAsync(d_ok, &hv, sizeof(double), cudaMemcpyHostToDevice, st));
+        comm_allreduce_max(d_ok, 1, COMM_WORLD, st);
+        EE_CUDA(cudaMemcpyAsync(&hv, d_ok, sizeof(double), cudaMemcpyDeviceToHost, st));
+        EE_CUDA(cudaStreamSynchronize(st));
+        dev_free(d_ok);
+        m->peer_ok = (hv == 0.0);
+        if (!m->peer_ok) {
+            if (r == 0) fprintf(stderr, "[eigenexa_b200] CUDA IPC peer ring unavailable; using NCCL all-reduce per column\n");
+            return false;
+        }
+    }
+    view->P = P; view->r = r; view->slot_doubles = m->peer_slot; view->err = m->peer_err;
+    for (int q = 0; q < P; q++) {
+        view->slots[q] = (double *)m->peer_ptr[q];
+        view->flags[q] = (unsigned long long *)((double *)m->peer_ptr[q] + (size_t)2 * P * m->peer_slot);
+    }
+    return true;
+}
+
+unsigned long long comm_peer_next_epoch() { return ++ctx().comm->epoch; }
+
 void comm_finalize()
 {
     Context &c = ctx();
     if (!c.comm) return;
+    peer_release(c.comm);
     for (int i = 2; i >= 0; i--)
         if (c.comm->c[i]) g_nccl.CommDestroy(c.comm->c[i]);
     delete c.comm;

@@ -24,4 +24,22 @@ void comm_group_start();
 void comm_group_end();
 void comm_barrier(cudaStream_t st);  // MPI_Barrier(TRD_COMM_WORLD)
 
+// ---- one-shot all-reduce over NVLink peer memory (fused into the trd vector kernels) --------
+// Every rank owns a buffer [2 parities][P slots][slot_doubles] + flags, mapped into all peers
+// with CUDA IPC.  A producer kernel stores its partial vector into slot[parity][my rank] of
+// EVERY rank and then publishes an epoch flag; the consumer kernel waits for the P flags and
+// sums the P slots in rank order (identical bits on every rank, as the reference's hand-made
+// reductions guarantee, src/comm.F:2100-2406).
+constexpr int PEER_MAX = 16;
+struct PeerView {
+    int P, r;
+    unsigned long long slot_doubles;
+    double *slots[PEER_MAX];                 // base of every rank's slot area (peer mapped)
+    unsigned long long *flags[PEER_MAX];     // base of every rank's flag area [2][P]
+    int *err;                                // local error flag (spin timeout)
+};
+// returns true when the peer ring is usable with at least slot_doubles per slot
+bool comm_peer_setup(size_t slot_doubles, PeerView *view);
+unsigned long long comm_peer_next_epoch();
+
 }  // namespace ee

@@ -279,8 +279,11 @@ __global__ void __launch_bounds__(256, 2) symv_kernel(TrdP P, int gx, int ntile_
 constexpr int VR = 32;   // rows per CTA in the vector kernels
 constexpr int VS = 8;    // slices per row
 
+// MODE 3 / 4 are MODE 1 / 2 with the cross-rank sum done over NVLink peer memory instead of an
+// NCCL call between the launches: 3 stores the partial into slot[parity][rank] of EVERY rank and
+// publishes an epoch flag; 4 waits for all P flags and sums the slots in rank order.
 template <int MODE>
-__global__ void __launch_bounds__(VR * VS) pvec_kernel(TrdP P)
+__global__ void __launch_bounds__(VR * VS) pvec_kernel(TrdP P, PeerView pv, unsigned long long epoch)
 {
     __shared__ double s_st[2 * MAXM];
     __shared__ int s_nbr[1024];
@@ -290,10 +293,24 @@ __global__ void __launch_bounds__(VR * VS) pvec_kernel(TrdP P)
     const int nd = P.ndone;
     const int nclL = ncl_of(P);
     const int nsc = nstrips_of(P, nclL);
-    if (MODE != 2) {
+    constexpr bool PARTIAL = (MODE == 0 || MODE == 1 || MODE == 3);   // sums the tile partials
+    constexpr bool FINISH = (MODE == 0 || MODE == 2 || MODE == 4);    // corrections + u^T p
+    const int par = (int)(epoch & 1ull);
+    if (MODE == 4 && threadIdx.x == 0) {
+        const volatile unsigned long long *fl = pv.flags[pv.r] + (size_t)par * pv.P;
+        for (int q = 0; q < pv.P; q++) {
+            unsigned long long spins = 0;
+            while (fl[q] < epoch) {
+                __nanosleep(64);
+                if (++spins > (1ull << 27)) { *pv.err = 1; break; }   // ~10 s: peer never arrived
+            }
+        }
+        __threadfence_system();
+    }
+    if (PARTIAL) {
         for (int s = threadIdx.x; s < nsc; s += blockDim.x) s_nbr[s] = strip_rows(P, s, nclL);
     }
-    if (MODE != 1) {
+    if (FINISH) {
         for (int c = threadIdx.x; c < 2 * nd; c += blockDim.x) s_st[c] = P.st[c];
     }
     __syncthreads();
@@ -301,7 +318,7 @@ __global__ void __launch_bounds__(VR * VS) pvec_kernel(TrdP P)
     const int g = blockIdx.x * VR + r;
     double acc = 0.0;
     if (g < P.L) {
-        if (MODE != 2) {
+        if (PARTIAL) {
             const bool rown = (g % P.px) == P.x, coln = (g % P.py) == P.y;
             if (rown) {
                 const int jl = g / P.px, br = jl / TR;
@@ -314,9 +331,12 @@ __global__ void __launch_bounds__(VR * VS) pvec_kernel(TrdP P)
                 if (rown && sl == 0) acc = fma(P.A[(size_t)il * P.lda + g / P.px], P.ucur[g], acc);
             }
         } else if (sl == 0) {
-            acc = P.pbuf[g];
+            if (MODE == 4) {
+                const double *base = pv.slots[pv.r] + (size_t)par * pv.P * pv.slot_doubles + g;
+                for (int q = 0; q < pv.P; q++) acc += __ldcg(base + (size_t)q * pv.slot_doubles);
+            } else acc = P.pbuf[g];
         }
-        if (MODE != 1) {
+        if (FINISH) {
             // corrections with the finished pairs of this panel
             for (int l = sl; l < nd; l += VS) {
                 const size_t off = (size_t)(P.k + 1 + l) * P.npad + g;
@@ -333,12 +353,30 @@ __global__ void __launch_bounds__(VR * VS) pvec_kernel(TrdP P)
 #pragma unroll
         for (int q = 0; q < VS; q++) p += s_acc[q][r];
         if (g < P.L) {
-            P.pbuf[g] = p;
-            if (MODE != 1) up = P.ucur[g] * p;
+            if (MODE == 3) {
+                const size_t off = ((size_t)par * pv.P + pv.r) * pv.slot_doubles + g;
+                for (int q = 0; q < pv.P; q++) pv.slots[q][off] = p;   // NVLink stores to every rank
+            } else P.pbuf[g] = p;
+            if (FINISH) up = P.ucur[g] * p;
         }
         up = warp_sum(up);
     }
     if (MODE == 1) return;
+    if (MODE == 3) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(&P.tickets[3], 1u);
+        __syncthreads();
+        if (s_last == gridDim.x - 1 && threadIdx.x == 0) {
+            __threadfence_system();
+            for (int q = 0; q < pv.P; q++) {
+                volatile unsigned long long *fl = pv.flags[q] + (size_t)par * pv.P + pv.r;
+                *fl = epoch;
+            }
+            P.tickets[3] = 0u;
+        }
+        return;
+    }
     if (threadIdx.x == 0) {
         P.part[blockIdx.x] = up;
         __threadfence();
@@ -687,6 +725,9 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
     P.d_out = d_out; P.e_out = e_out;
     double *UVx = ws + oUVx, *VUy = ws + oVUy;
     const bool multi = g.nnod > 1;
+    PeerView pv;
+    memset(&pv, 0, sizeof pv);
+    const bool use_peer = multi && comm_peer_setup((size_t)npad, &pv);
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float t_symv = 0.f, t_syr2k = 0.f, t_pvec = 0.f, t_vvec = 0.f;
@@ -794,13 +835,19 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
             const int nvb = (L + VR - 1) / VR;
             prof_begin();
             if (!multi) {
-                pvec_kernel<0><<<nvb, VR * VS, 0, st>>>(Q);
+                pvec_kernel<0><<<nvb, VR * VS, 0, st>>>(Q, pv, 0ull);
+                EE_CHECK_LAUNCH();
+            } else if (use_peer) {
+                const unsigned long long epoch = comm_peer_next_epoch();
+                pvec_kernel<3><<<nvb, VR * VS, 0, st>>>(Q, pv, epoch);
+                EE_CHECK_LAUNCH();
+                pvec_kernel<4><<<nvb, VR * VS, 0, st>>>(Q, pv, epoch);
                 EE_CHECK_LAUNCH();
             } else {
-                pvec_kernel<1><<<nvb, VR * VS, 0, st>>>(Q);
+                pvec_kernel<1><<<nvb, VR * VS, 0, st>>>(Q, pv, 0ull);
                 EE_CHECK_LAUNCH();
                 comm_allreduce_sum(P.pbuf, L, COMM_WORLD, st);
-                pvec_kernel<2><<<nvb, VR * VS, 0, st>>>(Q);
+                pvec_kernel<2><<<nvb, VR * VS, 0, st>>>(Q, pv, 0ull);
                 EE_CHECK_LAUNCH();
             }
             prof_end(t_pvec);
@@ -849,6 +896,11 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
         EE_CUDA(cudaMemcpy2DAsync(a_user, (size_t)lda_user * sizeof(double), A, (size_t)lda * sizeof(double),
                                   (size_t)nrl * sizeof(double), ncl, cudaMemcpyDeviceToDevice, st));
     EE_CUDA(cudaStreamSynchronize(st));
+    if (use_peer) {
+        int herr = 0;
+        EE_CUDA(cudaMemcpy(&herr, pv.err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (herr) fatal("peer all-reduce timed out waiting for another rank", __FILE__, __LINE__);
+    }
     double tw3 = wall();
     if (c.profiling == 1) {
         auto drain = [&](std::vector<cudaEvent_t> &pool, float &acc, bool trace) {
