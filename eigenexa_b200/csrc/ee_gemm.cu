@@ -254,13 +254,27 @@ void launch_cfg(cudaStream_t st, const GemmP &p, bool al16)
     EE_CHECK_LAUNCH();
 }
 
+static int gemm_cfg()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("EIGENEXA_B200_GEMM_CFG"); v = e ? atoi(e) : 0; }
+    return v;
+}
+
 template <bool AK, bool BK>
 void launch_layout(cudaStream_t st, const GemmP &p, bool al16)
 {
-    // 128x128 tiles (1 CTA/SM, 8 warps) for deep-K problems, 128x64 (2 CTA/SM) when the
-    // C read-modify-write has to overlap with another CTA's math (small K)
-    if (p.K / p.ksplit >= 512 && p.beta == 0.0) launch_cfg<128, 128, 2, 4, AK, BK, 1>(st, p, al16);
-    else launch_cfg<128, 64, 2, 4, AK, BK, 2>(st, p, al16);
+    // measured on B200 (tools/gemm_sweep.py, profiles/r01_gemm_sweep.md): 128x64 tiles with 16
+    // warps per CTA and 2 CTAs/SM (32 resident warps hide the LDS->DMMA and barrier latency)
+    // beat the 8-warp 128x128 / 128x64 variants on every shape of the path.
+    const int cfg = gemm_cfg();
+    if (cfg == 1) { launch_cfg<128, 128, 4, 4, AK, BK, 1>(st, p, al16); return; }
+    if (cfg == 4) {
+        if (p.K / p.ksplit >= 512 && p.beta == 0.0) launch_cfg<128, 128, 2, 4, AK, BK, 1>(st, p, al16);
+        else launch_cfg<128, 64, 2, 4, AK, BK, 2>(st, p, al16);
+        return;
+    }
+    launch_cfg<128, 64, 4, 4, AK, BK, 2>(st, p, al16);
 }
 
 }  // namespace

@@ -13,6 +13,7 @@
 // x group, as in trbakwy4_body.F:235.
 #include "ee_common.cuh"
 #include "ee_comm.h"
+#include <chrono>
 
 namespace ee {
 
@@ -132,6 +133,8 @@ void trbak_dev(int n, int nvec, const double *a, int lda, double *z, int ldz, co
     const int ldv = (n + 15) & ~15;
     const int nrl_max = cyc_count(n, g.px, g.x);
     const int ldvx = ((nrl_max > 0 ? nrl_max : 1) + 15) & ~15;
+    auto wall = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double hw0 = wall();
     double *V = (double *)dev_alloc((size_t)ldv * mb * sizeof(double));
     double *Vx = (g.px > 1) ? (double *)dev_alloc((size_t)ldvx * mb * sizeof(double)) : V;
     double *SMp = (double *)dev_alloc((size_t)KSPLIT * mb * mb * sizeof(double));
@@ -145,6 +148,18 @@ void trbak_dev(int n, int nvec, const double *a, int lda, double *z, int ldz, co
     double *SS2 = (double *)dev_alloc(ss_elems * sizeof(double));
     EE_CUDA(cudaFuncSetAttribute(tinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TB * (TB + 1) * sizeof(double))));
 
+    const double hw1 = wall();
+    // profiling level 2: per-class device time (sync per class) -> timings[22..27]
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    double tcls[6] = {0, 0, 0, 0, 0, 0};
+    if (c.profiling >= 2) { EE_CUDA(cudaEventCreate(&pe0)); EE_CUDA(cudaEventCreate(&pe1)); }
+    auto pb = [&]() { if (c.profiling >= 2) EE_CUDA(cudaEventRecord(pe0, st)); };
+    auto pe = [&](int cls) {
+        if (c.profiling >= 2) {
+            EE_CUDA(cudaEventRecord(pe1, st)); EE_CUDA(cudaEventSynchronize(pe1));
+            float ms; EE_CUDA(cudaEventElapsedTime(&ms, pe0, pe1)); tcls[cls] += ms * 1e-3;
+        }
+    };
     // reflector columns i = 1..n-1 ; first block takes the remainder (trbakwy4.F:292)
     int i0 = 1;
     int first = (n - 1) % mb;
@@ -153,6 +168,7 @@ void trbak_dev(int n, int nvec, const double *a, int lda, double *z, int ldz, co
         const int rows = i0 + cur - 1;  // longest reflector of the block
         const int nrl = cyc_count(rows, g.px, g.x);
         // ---- V panel (K15) ---------------------------------------------------------------
+        pb();
         {
             dim3 grid((ldv + 255) / 256, cur);
             gather_v_kernel<<<grid, 256, 0, st>>>(a, lda, g.px, g.py, g.x, g.y, i0, cur, rows, V, ldv);
@@ -164,7 +180,9 @@ void trbak_dev(int n, int nvec, const double *a, int lda, double *z, int ldz, co
                 EE_CHECK_LAUNCH();
             }
         }
+        pe(0);
         const int ldx = (g.px > 1) ? ldvx : ldv;
+        pb();
         // ---- S = -V^T V from the replicated panel (split-K partials), T = S^{-1} (K12,K13) ---
         int ks = rows / 512; if (ks < 1) ks = 1; if (ks > KSPLIT) ks = KSPLIT;
         dgemm_ex(st, 'T', 'N', cur, cur, rows, 1.0, V, ldv, V, ldv, 0.0, SMp, cur, ks, (long long)cur * cur);
@@ -180,11 +198,13 @@ void trbak_dev(int n, int nvec, const double *a, int lda, double *z, int ldz, co
             dgemm(st, 'N', 'N', b2, b1, b1, 1.0, S + b1, cur, T, cur, 0.0, Wt, b2);
             dgemm(st, 'N', 'N', b2, b1, b2, -1.0, T + (size_t)b1 * cur + b1, cur, Wt, b2, 0.0, T + b1, cur);
         }
+        pe(1);
         if (nvl > 0) {
+            pb();
             // ---- SS = Vx^T Z  (K12), split-K sized to fill the last wave ; x-group sum (C13) -----
             if (nrl > 0) {
-                const long long tiles = (long long)((cur + 127) / 128) * ((nvl + 127) / 128);
-                const int sk = choose_ksplit(tiles, nrl, c.sm_count);
+                const long long tiles = (long long)((cur + 127) / 128) * ((nvl + 63) / 64);
+                const int sk = choose_ksplit(tiles, nrl, 2 * c.sm_count);
                 if (sk == 1) dgemm(st, 'T', 'N', cur, nvl, nrl, 1.0, Vx, ldx, z, ldz, 0.0, SS, ldss);
                 else {
                     dgemm_ex(st, 'T', 'N', cur, nvl, nrl, 1.0, Vx, ldx, z, ldz, 0.0, SSp, ldss, sk, (long long)ss_elems);
@@ -193,15 +213,28 @@ void trbak_dev(int n, int nvec, const double *a, int lda, double *z, int ldz, co
                 }
             } else EE_CUDA(cudaMemsetAsync(SS, 0, (size_t)ldss * nvl * sizeof(double), st));
             if (g.px > 1) comm_allreduce_sum(SS, (size_t)ldss * nvl, COMM_X, st);
+            pe(2);
             // ---- SS2 = T SS ; Z += Vx SS2  (K14) ---------------------------------------------
+            pb();
             dgemm(st, 'N', 'N', cur, nvl, cur, 1.0, T, cur, SS, ldss, 0.0, SS2, ldss);
+            pe(3);
+            pb();
             if (nrl > 0) dgemm(st, 'N', 'N', nrl, nvl, cur, 1.0, Vx, ldx, SS2, ldss, 1.0, z, ldz);
+            pe(4);
         }
         i0 += cur;
     }
+    const double hw2 = wall();
     EE_CUDA(cudaStreamSynchronize(st));
+    const double hw3 = wall();
+    c.timings[27] = hw1 - hw0; c.timings[28] = hw2 - hw1; c.timings[29] = hw3 - hw2;
+    if (c.profiling >= 2) {
+        for (int i = 0; i < 5; i++) c.timings[22 + i] = tcls[i];
+        cudaEventDestroy(pe0); cudaEventDestroy(pe1);
+    }
     dev_free(V); if (g.px > 1) dev_free(Vx);
     dev_free(SMp); dev_free(S); dev_free(T); dev_free(Wt); dev_free(SSp); dev_free(SS); dev_free(SS2);
+    c.timings[30] = wall() - hw3;
 }
 
 }  // namespace ee
