@@ -45,6 +45,8 @@ def lib() -> C.CDLL:
             f.restype = None
         L.eigenexa_b200_eigen_s_dev.argtypes = L.eigen_s.argtypes
         L.eigenexa_b200_eigen_s_dev.restype = C.c_int
+        L.eigenexa_b200_eigen_sx_dev.argtypes = L.eigen_s.argtypes
+        L.eigenexa_b200_eigen_sx_dev.restype = C.c_int
         L.eigen_get_matdims.argtypes = [C.c_int, ip, ip, C.c_int, C.c_int, C.c_char_p]
         L.eigen_get_procs.argtypes = [ip, ip, ip]
         L.eigen_get_id.argtypes = [ip, ip, ip]
@@ -62,6 +64,10 @@ def lib() -> C.CDLL:
         L.eigenexa_b200_trbakwy.argtypes = [C.c_int, C.c_int, dp, C.c_int, dp, C.c_int, dp, C.c_int]
         L.eigenexa_b200_dc.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, C.c_int]
         L.eigenexa_b200_bisect.argtypes = [C.c_int, dp, dp, dp]
+        L.eigenexa_b200_prd.argtypes = [C.c_int, dp, C.c_int, dp, dp, C.c_int, C.c_int]
+        L.eigenexa_b200_dcx.argtypes = [C.c_int, C.c_int, dp, dp, C.c_int, dp, dp, C.c_int]
+        L.eigenexa_b200_bisect2.argtypes = [C.c_int, dp, dp, C.c_int, dp]
+        L.eigenexa_b200_trbakwy_nb.argtypes = [C.c_int, C.c_int, dp, C.c_int, dp, C.c_int, dp, C.c_int, C.c_int]
         L.eigenexa_b200_mat_set_dev.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint64]
         L.eigenexa_b200_mat_set_host.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint64]
         L.eigenexa_b200_ev_test_dev.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
@@ -201,6 +207,14 @@ def eigen_s_dev(n, a_ptr, lda, w_ptr, z_ptr, ldz, nvec=None, m_forward=48, m_bac
         raise RuntimeError(last_error())
 
 
+def eigen_sx_dev(n, a_ptr, lda, w_ptr, z_ptr, ldz, nvec=None, m_forward=48, m_backward=128, mode="A") -> None:
+    """eigen_sx with device pointers (penta-diagonal path)."""
+    rc = lib().eigenexa_b200_eigen_sx_dev(n, n if nvec is None else nvec, a_ptr, lda, w_ptr, z_ptr, ldz, m_forward,
+                                          m_backward, mode.encode()[:1])
+    if rc != 0:
+        raise RuntimeError(last_error())
+
+
 # ---------------------------------------------------------------------------------------
 # stage-level procedures (eigen_trd_mod, trbakwy4_mod, dc2, bisect)
 # ---------------------------------------------------------------------------------------
@@ -214,12 +228,43 @@ def eigen_trd(n, a, m_forward=48):
     return d, e
 
 
-def eigen_trbakwy(n, a, z, e, m_backward=128, nvec=None):
-    """eigen_common_trbakwy(n, nvec, a, lda, z, ldz, e, m, 1) (src/trbakwy4.F:77); z in place."""
+def eigen_prd(n, a, m_forward=48):
+    """eigen_prd(n, a, lda, d, e, ne, m) (src/eigen_prd.F:80): returns (d, e1, e2); a <- reflectors."""
+    _check_f(a, "a")
+    d, e = np.zeros(n), np.zeros((2, n))
+    rc = lib().eigenexa_b200_prd(n, _dp(a), a.shape[0], _dp(d), _dp(e), n, m_forward)
+    if rc != 0:
+        raise RuntimeError(f"eigen_prd rc={rc}: {last_error()}")
+    return d, e[0].copy(), e[1].copy()
+
+
+def eigen_dcx(n, d, e1, e2, z, nvec=None):
+    """Penta-diagonal eigen-decomposition (eigen_dcx, src/dcx.F:75).  Returns w; z filled in place."""
+    _check_f(z, "z")
+    w = np.zeros(n)
+    e = np.ascontiguousarray(np.stack([e1, e2]))
+    rc = lib().eigenexa_b200_dcx(n, n if nvec is None else nvec, _dp(np.ascontiguousarray(d)), _dp(e), n, _dp(w), _dp(z),
+                                 z.shape[0])
+    if rc != 0:
+        raise RuntimeError(f"eigen_dcx rc={rc}: {last_error()}")
+    return w
+
+
+def eigen_bisect2(n, d, e1, e2):
+    w = np.zeros(n)
+    e = np.ascontiguousarray(np.stack([e1, e2]))
+    rc = lib().eigenexa_b200_bisect2(n, _dp(np.ascontiguousarray(d)), _dp(e), n, _dp(w))
+    if rc != 0:
+        raise RuntimeError(f"eigen_bisect2 rc={rc}: {last_error()}")
+    return w
+
+
+def eigen_trbakwy(n, a, z, e, m_backward=128, nvec=None, nb=1):
+    """eigen_common_trbakwy(n, nvec, a, lda, z, ldz, e, m, nb) (src/trbakwy4.F:77); z in place."""
     _check_f(a, "a")
     _check_f(z, "z")
-    rc = lib().eigenexa_b200_trbakwy(n, n if nvec is None else nvec, _dp(a), a.shape[0], _dp(z), z.shape[0],
-                                     _dp(np.ascontiguousarray(e)), m_backward)
+    rc = lib().eigenexa_b200_trbakwy_nb(n, n if nvec is None else nvec, _dp(a), a.shape[0], _dp(z), z.shape[0],
+                                        _dp(np.ascontiguousarray(e)), m_backward, nb)
     if rc != 0:
         raise RuntimeError(f"eigen_trbakwy rc={rc}: {last_error()}")
     return z

@@ -81,7 +81,88 @@ __global__ void monotone_fix_kernel(int n, double *w)
         if (w[i] < w[i - 1]) w[i] = w[i - 1];
 }
 
+// ---- penta-diagonal: inertia of T - x I from the banded L D L^T recurrence ---------------------
+//   l2 = a(i,i-2)/q(i-2) ; t = a(i,i-1) - a(i,i-2) l(i-1,i-2) ; l1 = t/q(i-1)
+//   q(i) = a(i,i) - x - l1 t - l2 a(i,i-2)
+// (eigen_bisect2 / sturm2_LDLT, src/bisect2.F:371-678, counts the negative pivots of the same
+// factorisation; its 2x2-pivot safeguard is replaced by the pivmin guard of the tridiagonal code.)
+__global__ void bisect2_prep_kernel(int n, const double *d, const double *e1, const double *e2, double *bounds)
+{
+    __shared__ double s_lo[256], s_hi[256], s_em[256];
+    double lo = d[0], hi = d[0], em = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double r = 0.0;
+        if (i > 0) r += fabs(e1[i]);
+        if (i > 1) r += fabs(e2[i]);
+        if (i + 1 < n) r += fabs(e1[i + 1]);
+        if (i + 2 < n) r += fabs(e2[i + 2]);
+        lo = fmin(lo, d[i] - r); hi = fmax(hi, d[i] + r);
+        em = fmax(em, r);
+    }
+    s_lo[threadIdx.x] = lo; s_hi[threadIdx.x] = hi; s_em[threadIdx.x] = em;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < blockDim.x; i++) { lo = fmin(lo, s_lo[i]); hi = fmax(hi, s_hi[i]); em = fmax(em, s_em[i]); }
+        const double eps = 2.220446049250313e-16;
+        double x = (fabs(lo) + fabs(hi)) * eps + eps * em;
+        bounds[0] = lo - x; bounds[1] = hi + x;
+        bounds[2] = 2.2250738585072014e-308 * fmax(1.0, em * em);
+    }
+}
+
+__device__ __forceinline__ int sturm2_count(int n, const double *__restrict__ d, const double *__restrict__ e1,
+                                            const double *__restrict__ e2, double x, double pivmin)
+{
+    int cnt = 0;
+    double q2 = 1.0, q1 = 1.0, lprev = 0.0;   // q(i-2), q(i-1), l(i-1,i-2)
+    for (int i = 0; i < n; i++) {
+        const double a2 = (i > 1) ? e2[i] : 0.0, a1 = (i > 0) ? e1[i] : 0.0;
+        const double l2 = a2 / q2;
+        const double t = a1 - a2 * lprev;
+        const double l1 = t / q1;
+        double q = d[i] - x - l1 * t - l2 * a2;
+        if (fabs(q) < pivmin) q = -pivmin;
+        cnt += (q < 0.0);
+        q2 = q1; q1 = q; lprev = l1;
+    }
+    return cnt;
+}
+
+__global__ void bisect2_kernel(int n, const double *__restrict__ d, const double *__restrict__ e1,
+                               const double *__restrict__ e2, const double *__restrict__ bounds, double *w)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double lb = bounds[0], ub = bounds[1];
+    const double pivmin = bounds[2];
+    double x = lb;
+    for (int it = 0; it < 2048; it++) {
+        double t = x;
+        x = 0.5 * (lb + ub);
+        if (x == t || x <= lb || x >= ub) break;
+        int s = sturm2_count(n, d, e1, e2, x, pivmin);
+        if (s <= k) lb = x; else ub = x;
+    }
+    w[k] = x;
+}
+
 }  // namespace
+
+void bisect2_dev(int n, const double *d, const double *e1, const double *e2, double *w)
+{
+    Context &c = ctx();
+    cudaStream_t st = c.stream;
+    if (n == 1) { EE_CUDA(cudaMemcpyAsync(w, d, sizeof(double), cudaMemcpyDeviceToDevice, st)); return; }
+    double *bounds = (double *)dev_alloc(sizeof(double) * 4);
+    bisect2_prep_kernel<<<1, 256, 0, st>>>(n, d, e1, e2, bounds);
+    EE_CHECK_LAUNCH();
+    bisect2_kernel<<<(n + 63) / 64, 64, 0, st>>>(n, d, e1, e2, bounds, w);
+    EE_CHECK_LAUNCH();
+    monotone_fix_kernel<<<1, 32, 0, st>>>(n, w);
+    EE_CHECK_LAUNCH();
+    EE_CUDA(cudaStreamSynchronize(st));
+    dev_free(bounds);
+}
 
 void bisect_dev(int n, const double *d, const double *e, double *w)
 {

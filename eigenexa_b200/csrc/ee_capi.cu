@@ -142,7 +142,6 @@ static void eigen_s_impl(int n, int nvec, double *a, int lda, double *w, double 
     c.errinfo = 0;
     if (!c.initialized) return;  // eigen_s.F:81-84
     if (n <= 0) { fprintf(stderr, "Warining: Negative dimesion is invalid!\n"); return; }
-    (void)penta;  // eigen_sx: same results through the tridiagonal path
     char mode = 'A';
     if (mode_in && mode_in[0]) mode = mode_in[0];
     if (mode >= 'a' && mode <= 'z') mode = (char)(mode - 'a' + 'A');
@@ -176,6 +175,7 @@ static void eigen_s_impl(int n, int nvec, double *a, int lda, double *w, double 
     const int lda_d = dev_ptrs ? lda : ldd;
     double *d_d = (double *)dev_alloc((size_t)n * sizeof(double));
     double *e_d = (double *)dev_alloc((size_t)n * sizeof(double));
+    double *e2_d = penta ? (double *)dev_alloc((size_t)n * sizeof(double)) : nullptr;
     T.mark(1);
     double ret1 = 0, ret2 = 0, ret3 = 0;
     // ---- scaling (eigen_s.F:155-160) --------------------------------------------------------
@@ -189,26 +189,30 @@ static void eigen_s_impl(int n, int nvec, double *a, int lda, double *w, double 
     }
     if (!done) {
         // ---- forward reduction (eigen_s.F:172-177) ------------------------------------------
-        trd_dev(n, a_d, lda_d, (mode == 'N') ? d_d : w_d, e_d, m_f);
+        // eigen_s: eigen_trd (eigen_s.F:172-177); eigen_sx: eigen_prd (eigen_sx.F:160-162)
+        if (penta) prd_dev(n, a_d, lda_d, (mode == 'N') ? d_d : w_d, e_d, e2_d, m_f);
+        else trd_dev(n, a_d, lda_d, (mode == 'N') ? d_d : w_d, e_d, m_f);
         ret1 = (double)n * n * n * 4.0 / 3.0;
         T.mark(2);
         if (mode == 'N') {
             // eigen_bisect(d,e,w,n,0); NB the reference jumps to the exit without undoing
             // the scaling in this mode (eigen_s.F:219-234) -- kept.
-            bisect_dev(n, d_d, e_d, w_d);
+            if (penta) bisect2_dev(n, d_d, e_d, e2_d, w_d);   // eigen_bisect2 (eigen_sx.F:219-221)
+            else bisect_dev(n, d_d, e_d, w_d);
             T.mark(3); T.mark(4);
         } else {
             // ---- tridiagonal eigensolver (eigen_s.F:197-213) ---------------------------------
             const int ldz_d = dev_ptrs ? ldz : ldd;
             if (!dev_ptrs) z_d = (double *)dev_alloc((size_t)ldz_d * (nvl > 0 ? nvl : 1) * sizeof(double));
             EE_CUDA(cudaMemcpyAsync(d_d, w_d, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-            int info = dc_dev(n, nv, d_d, e_d, w_d, z_d, ldz_d);
+            int info = penta ? dc_band_dev(n, nv, d_d, e_d, e2_d, w_d, z_d, ldz_d)      // eigen_dcx (eigen_sx.F:209)
+                             : dc_dev(n, nv, d_d, e_d, w_d, z_d, ldz_d);
             c.errinfo = info;
             ret2 = c.timings[13] > 0 ? c.timings[13] : 1.0;  // merge GEMM flops (mx_pdlaed1.F:291,304); > 0 keeps ret positive
-            if (mode == 'X') bisect_dev(n, d_d, e_d, w_d);
+            if (mode == 'X') { if (penta) bisect2_dev(n, d_d, e_d, e2_d, w_d); else bisect_dev(n, d_d, e_d, w_d); }
             T.mark(3);
             // ---- back-transformation (eigen_s.F:245-248) ------------------------------------
-            trbak_dev(n, nv, a_d, lda_d, z_d, ldz_d, e_d, m_b);
+            trbak_dev(n, nv, a_d, lda_d, z_d, ldz_d, penta ? e2_d : e_d, m_b, penta ? 2 : 1);   // nb = MBAND (eigen_sx.F:245)
             ret3 = 2.0 * (double)nv * (double)n * (double)n;
             // ---- undo the scaling (eigen_s.F:261-264) ---------------------------------------
             if (sigma != 1.0 && sigma != 0.0) {
@@ -238,7 +242,7 @@ static void eigen_s_impl(int n, int nvec, double *a, int lda, double *w, double 
             else memcpy(a, stats, cnt * sizeof(double));
         }
     }
-    dev_free(d_d); dev_free(e_d);
+    dev_free(d_d); dev_free(e_d); if (e2_d) dev_free(e2_d);
     if (!dev_ptrs) { dev_free(a_d); dev_free(w_d); if (z_d) dev_free(z_d); }
 }
 
@@ -330,6 +334,13 @@ int eigenexa_b200_eigen_s_dev(int n, int nvec, double *a_dev, int lda, double *w
 {
     if (!ctx().initialized) { set_error("not initialised"); return 1; }
     eigen_s_impl(n, nvec, a_dev, lda, w_dev, z_dev, ldz, m_forward, m_backward, mode, true, false);
+    return 0;
+}
+int eigenexa_b200_eigen_sx_dev(int n, int nvec, double *a_dev, int lda, double *w_dev, double *z_dev, int ldz,
+                               int m_forward, int m_backward, const char *mode)
+{
+    if (!ctx().initialized) { set_error("not initialised"); return 1; }
+    eigen_s_impl(n, nvec, a_dev, lda, w_dev, z_dev, ldz, m_forward, m_backward, mode, true, true);
     return 0;
 }
 
@@ -434,7 +445,15 @@ int eigenexa_b200_trd(int n, double *a, int lda, double *d, double *e, int m_for
     return 0;
 }
 
+int eigenexa_b200_trbakwy_nb(int n, int nvec, const double *a, int lda, double *z, int ldz, const double *e,
+                             int m_backward, int nb);
 int eigenexa_b200_trbakwy(int n, int nvec, const double *a, int lda, double *z, int ldz, const double *e, int m_backward)
+{
+    return eigenexa_b200_trbakwy_nb(n, nvec, a, lda, z, ldz, e, m_backward, 1);
+}
+
+int eigenexa_b200_trbakwy_nb(int n, int nvec, const double *a, int lda, double *z, int ldz, const double *e,
+                             int m_backward, int nb)
 {
     Context &c = ctx();
     if (!c.initialized) { set_error("not initialised"); return 1; }
@@ -453,11 +472,82 @@ int eigenexa_b200_trbakwy(int n, int nvec, const double *a, int lda, double *z, 
         EE_CUDA(cudaMemcpy2DAsync(z_d, (size_t)ldd * 8, z, (size_t)ldz * 8, (size_t)nrl * 8, nvl, cudaMemcpyHostToDevice, c.stream));
     EE_CUDA(cudaMemcpyAsync(e_d, e, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
     int m = m_backward <= 0 ? 128 : m_backward;
-    trbak_dev(n, nvec < n ? nvec : n, a_d, ldd, z_d, ldd, e_d, m);
+    trbak_dev(n, nvec < n ? nvec : n, a_d, ldd, z_d, ldd, e_d, m, nb == 2 ? 2 : 1);
     if (nrl > 0 && nvl > 0)
         EE_CUDA(cudaMemcpy2DAsync(z, (size_t)ldz * 8, z_d, (size_t)ldd * 8, (size_t)nrl * 8, nvl, cudaMemcpyDeviceToHost, c.stream));
     EE_CUDA(cudaStreamSynchronize(c.stream));
     dev_free(a_d); dev_free(z_d); dev_free(e_d);
+    return 0;
+}
+
+// eigen_prd(n, a, lda, d, e, ne, m)  (src/eigen_prd.F:80): e is (ne x 2), e(:,1) first, e(:,2) second off-diagonal
+int eigenexa_b200_prd(int n, double *a, int lda, double *d, double *e, int ne, int m_forward)
+{
+    Context &c = ctx();
+    if (!c.initialized) { set_error("not initialised"); return 1; }
+    if (n <= 0) return 2;
+    const Grid &g = c.g;
+    const int nrl = cyc_count(n, g.px, g.x), ncl = cyc_count(n, g.py, g.y);
+    if (lda < nrl || ne < n) return 3;
+    const int ldd = nrl > 0 ? nrl : 1;
+    double *a_d = (double *)dev_alloc((size_t)ldd * (ncl > 0 ? ncl : 1) * sizeof(double));
+    double *d_d = (double *)dev_alloc(sizeof(double) * n), *e_d = (double *)dev_alloc(sizeof(double) * 2 * n);
+    if (nrl > 0 && ncl > 0)
+        EE_CUDA(cudaMemcpy2DAsync(a_d, (size_t)ldd * 8, a, (size_t)lda * 8, (size_t)nrl * 8, ncl, cudaMemcpyHostToDevice, c.stream));
+    int m = m_forward <= 0 ? 48 : m_forward;
+    prd_dev(n, a_d, ldd, d_d, e_d, e_d + n, m);
+    if (nrl > 0 && ncl > 0)
+        EE_CUDA(cudaMemcpy2DAsync(a, (size_t)lda * 8, a_d, (size_t)ldd * 8, (size_t)nrl * 8, ncl, cudaMemcpyDeviceToHost, c.stream));
+    EE_CUDA(cudaMemcpyAsync(d, d_d, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+    EE_CUDA(cudaMemcpyAsync(e, e_d, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+    EE_CUDA(cudaMemcpyAsync(e + ne, e_d + n, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+    EE_CUDA(cudaStreamSynchronize(c.stream));
+    dev_free(a_d); dev_free(d_d); dev_free(e_d);
+    return 0;
+}
+
+// eigen_dcx (src/dcx.F:75): penta-diagonal (d, e(:,1), e(:,2)) -> w, z
+int eigenexa_b200_dcx(int n, int nvec, const double *d, const double *e, int ne, double *w, double *z, int ldz)
+{
+    Context &c = ctx();
+    if (!c.initialized) { set_error("not initialised"); return 1; }
+    if (n <= 0 || ne < n) return 2;
+    const Grid &g = c.g;
+    const int nrl = cyc_count(n, g.px, g.x);
+    const int nv = nvec <= 0 || nvec > n ? n : nvec;
+    const int nvl = cyc_count(nv, g.py, g.y);
+    if (ldz < nrl) return 3;
+    const int ldd = nrl > 0 ? nrl : 1;
+    double *z_d = (double *)dev_alloc((size_t)ldd * (nvl > 0 ? nvl : 1) * 8);
+    double *d_d = (double *)dev_alloc(sizeof(double) * n), *e_d = (double *)dev_alloc(sizeof(double) * 2 * n);
+    double *w_d = (double *)dev_alloc(sizeof(double) * n);
+    EE_CUDA(cudaMemcpyAsync(d_d, d, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+    EE_CUDA(cudaMemcpyAsync(e_d, e, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+    EE_CUDA(cudaMemcpyAsync(e_d + n, e + ne, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+    int info = dc_band_dev(n, nv, d_d, e_d, e_d + n, w_d, z_d, ldd);
+    if (nrl > 0 && nvl > 0)
+        EE_CUDA(cudaMemcpy2DAsync(z, (size_t)ldz * 8, z_d, (size_t)ldd * 8, (size_t)nrl * 8, nvl, cudaMemcpyDeviceToHost, c.stream));
+    EE_CUDA(cudaMemcpyAsync(w, w_d, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+    EE_CUDA(cudaStreamSynchronize(c.stream));
+    dev_free(z_d); dev_free(d_d); dev_free(e_d); dev_free(w_d);
+    return info;
+}
+
+// eigen_bisect2 (src/bisect2.F:71)
+int eigenexa_b200_bisect2(int n, const double *d, const double *e, int ne, double *w)
+{
+    Context &c = ctx();
+    if (!c.initialized) { set_error("not initialised"); return 1; }
+    if (n <= 0 || ne < n) return 2;
+    double *d_d = (double *)dev_alloc(sizeof(double) * n), *e_d = (double *)dev_alloc(sizeof(double) * 2 * n);
+    double *w_d = (double *)dev_alloc(sizeof(double) * n);
+    EE_CUDA(cudaMemcpyAsync(d_d, d, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+    EE_CUDA(cudaMemcpyAsync(e_d, e, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+    EE_CUDA(cudaMemcpyAsync(e_d + n, e + ne, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+    bisect2_dev(n, d_d, e_d, e_d + n, w_d);
+    EE_CUDA(cudaMemcpyAsync(w, w_d, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+    EE_CUDA(cudaStreamSynchronize(c.stream));
+    dev_free(d_d); dev_free(e_d); dev_free(w_d);
     return 0;
 }
 

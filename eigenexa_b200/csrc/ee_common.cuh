@@ -84,11 +84,16 @@ double scaling_dev(int n, double *a, int lda);
 // eigen_trd: a (lda x ncl) in/out, d_out/e_out device arrays of length n (replicated)
 void trd_dev(int n, double *a, int lda, double *d_out, double *e_out, int m_forward);
 // eigen_common_trbakwy with z distributed 2D cyclic (ldz x nvl)
-void trbak_dev(int n, int nvec, const double *a, int lda, double *z, int ldz, const double *e, int m_backward);
+void trbak_dev(int n, int nvec, const double *a, int lda, double *z, int ldz, const double *e, int m_backward, int iblk = 1);
+// eigen_prd (penta-diagonal reduction): e1(i) = T(i-1,i), e2(i) = T(i-2,i)
+void prd_dev(int n, double *a, int lda, double *d_out, double *e1_out, double *e2_out, int m_forward);
 // tridiagonal divide and conquer; z (ldz x nvl) receives the local cyclic part
 int dc_dev(int n, int nvec, const double *d, const double *e, double *w, double *z, int ldz);
+// same for the penta-diagonal matrix (d, e, e2) of eigen_prd (eigen_dcx, src/dcx.F:75)
+int dc_band_dev(int n, int nvec, const double *d, const double *e, const double *e2, double *w, double *z, int ldz);
 // bisection
 void bisect_dev(int n, const double *d, const double *e, double *w);
+void bisect2_dev(int n, const double *d, const double *e1, const double *e2, double *w);   // penta-diagonal
 // mat_set / ev_test
 void mat_set_dev(int n, double *a, int lda, int mtype, uint64_t seed);
 void ev_test_dev(int n, int nvec, const double *a, int lda, const double *w, const double *z, int ldz, double *out);

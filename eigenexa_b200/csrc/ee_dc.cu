@@ -18,6 +18,15 @@
 //                      diag(Q1,Q2) (column types 1/2/3 as in dlaed2), i.e. half the flops.
 // The eigenvector matrix is never sorted physically between levels; an index permutation is
 // carried on the host and applied once when the caller's cyclic z is written.
+//
+// The same code solves the penta-diagonal matrix of eigen_prd (eigen_dcx, src/dcx.F:75,
+// my_pdsxedc.F, my_pdlaed0.F:226-391): the coupling between the halves of a split at row m is the
+// 2x2 block B = [T(m-2,m) 0 ; T(m-1,m) T(m-1,m+1)], i.e. the sum of two rank-one terms
+//     sigma_1 x_1 e_m^T       x_1 = (T(m-2,m), T(m-1,m)) / sigma_1   on rows (m-2, m-1)
+//     sigma_2 (+-e_{m-1}) e_{m+1}^T                                   sigma_2 = |T(m-1,m+1)|
+// and sigma (x y^T + y x^T) = sigma [(x+y)(x+y)^T - x x^T - y y^T], so every merge is two
+// successive rank-one updates: the first on the block-diagonal diag(Q1,Q2) (structured GEMM, as
+// in the tridiagonal case, which is sigma_2 = 0), the second on the dense merged matrix.
 #include "ee_common.cuh"
 #include "ee_comm.h"
 #include <numeric>
@@ -38,7 +47,7 @@ constexpr double HALF_EPS = 1.1102230246251565e-16;
 struct LeafDesc { int lo, sz; };
 
 __global__ void __launch_bounds__(32) leaf_jacobi_kernel(const LeafDesc *leaves, const double *d, const double *e,
-                                                         double *Q, long long ldq, double *dout)
+                                                         const double *e2, double *Q, long long ldq, double *dout)
 {
     __shared__ double A[LEAF][LEAF + 1];
     __shared__ double V[LEAF][LEAF + 1];
@@ -52,6 +61,7 @@ __global__ void __launch_bounds__(32) leaf_jacobi_kernel(const LeafDesc *leaves,
     if (lane < s) {
         A[lane][lane] = d[L.lo + lane];
         if (lane > 0) { double t = e[L.lo + lane]; A[lane][lane - 1] = t; A[lane - 1][lane] = t; }
+        if (e2 && lane > 1) { double t = e2[L.lo + lane]; A[lane][lane - 2] = t; A[lane - 2][lane] = t; }
     }
     __syncwarp();
     double nf = 0.0;
@@ -127,13 +137,18 @@ __global__ void __launch_bounds__(32) leaf_jacobi_kernel(const LeafDesc *leaves,
     }
 }
 
-// z = [last row of Q1 , first row of Q2] of the block at (lo, lo)
-__global__ void gather_z_kernel(const double *Q, long long ldq, int lo, int n1, int ns, double *z)
+// z = Q_node^T w for a vector w with (at most) four non-zeros: rows m-2 .. m+1 around the split
+struct ZSpec { int row[4]; double coef[4]; };
+__global__ void gather_z_kernel(const double *Q, long long ldq, int lo, int ns, ZSpec zs, double *z)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= ns) return;
-    int row = (j < n1) ? lo + n1 - 1 : lo + n1;
-    z[j] = Q[(long long)(lo + j) * ldq + row];
+    const double *col = Q + (long long)(lo + j) * ldq;
+    double s = 0.0;
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+        if (zs.coef[t] != 0.0) s = fma(zs.coef[t], col[zs.row[t]], s);
+    z[j] = s;
 }
 
 struct Rot { int p, q; double c, s; };
@@ -339,7 +354,16 @@ void build_tree(int lo, int hi, std::vector<Node> &merges, std::vector<LeafDesc>
 
 }  // namespace
 
+int dc_band_dev(int n, int nvec, const double *d_in, const double *e_in, const double *e2_in, double *w_out, double *z,
+                int ldz);
 int dc_dev(int n, int nvec, const double *d_in, const double *e_in, double *w_out, double *z, int ldz)
+{
+    return dc_band_dev(n, nvec, d_in, e_in, nullptr, w_out, z, ldz);
+}
+
+// e_in(i) = T(i-1,i); e2_in(i) = T(i-2,i) or nullptr for a tridiagonal matrix
+int dc_band_dev(int n, int nvec, const double *d_in, const double *e_in, const double *e2_in, double *w_out, double *z,
+                int ldz)
 {
     Context &c = ctx();
     const Grid &g = c.g;
@@ -347,18 +371,41 @@ int dc_dev(int n, int nvec, const double *d_in, const double *e_in, double *w_ou
     const int nrl = cyc_count(n, g.px, g.x);
     const int nvl = cyc_count(nvec, g.py, g.y);
 
-    std::vector<double> hd(n), he(n);
+    const bool penta = e2_in != nullptr;
+    std::vector<double> hd(n), he(n), he2(n, 0.0);
     EE_CUDA(cudaMemcpyAsync(hd.data(), d_in, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     EE_CUDA(cudaMemcpyAsync(he.data(), e_in, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    if (penta) EE_CUDA(cudaMemcpyAsync(he2.data(), e2_in, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     EE_CUDA(cudaStreamSynchronize(st));
     for (int i = 0; i < n; i++)
-        if (!std::isfinite(hd[i]) || !std::isfinite(he[i])) { set_error("dc: non-finite tridiagonal"); return 1; }
+        if (!std::isfinite(hd[i]) || !std::isfinite(he[i]) || !std::isfinite(he2[i])) { set_error("dc: non-finite band matrix"); return 1; }
 
     std::vector<Node> merges;
     std::vector<LeafDesc> leaves;
     build_tree(0, n, merges, leaves);
-    // rank-one tearing at every split point: d(mid-1) -= |e(mid)|, d(mid) -= |e(mid)|
-    for (const Node &m : merges) { double r = fabs(he[m.mid]); hd[m.mid - 1] -= r; hd[m.mid] -= r; }
+    // tearing at every split point m (blocks are >= 16 rows, so the touched entries never overlap):
+    //   first term : sigma_1 = |(T(m-2,m), T(m-1,m))|, x = that vector / sigma_1 on rows (m-2,m-1), y = e_m
+    //   second term: sigma_2 = |T(m-1,m+1)|, x = +-e_{m-1}, y = e_{m+1}
+    // diag(T1,T2) loses sigma x x^T and sigma y y^T  (tridiagonal: d(m-1) -= |e|, d(m) -= |e|)
+    struct Tear { double sig1, x0, x1, sig2, s2; };
+    std::vector<Tear> tears(merges.size());
+    for (size_t t = 0; t < merges.size(); t++) {
+        const int m = merges[t].mid;
+        Tear tr = {0, 0, 0, 0, 0};
+        const double b0 = he2[m], b1 = he[m];
+        tr.sig1 = hypot(b0, b1);
+        if (tr.sig1 > 0.0) {
+            tr.x0 = b0 / tr.sig1; tr.x1 = b1 / tr.sig1;
+            if (b0 != 0.0) { hd[m - 2] -= tr.sig1 * tr.x0 * tr.x0; he[m - 1] -= tr.sig1 * tr.x0 * tr.x1; }
+            hd[m - 1] -= tr.sig1 * tr.x1 * tr.x1;
+            hd[m] -= tr.sig1;
+        }
+        if (penta && m + 1 < merges[t].hi && he2[m + 1] != 0.0) {
+            tr.sig2 = fabs(he2[m + 1]); tr.s2 = he2[m + 1] > 0.0 ? 1.0 : -1.0;
+            hd[m - 1] -= tr.sig2; hd[m + 1] -= tr.sig2;
+        }
+        tears[t] = tr;
+    }
 
     const long long ldq = ((long long)n + 15) & ~15LL;
     const size_t qbytes = (size_t)ldq * n * sizeof(double);
@@ -374,19 +421,20 @@ int dc_dev(int n, int nvec, const double *d_in, const double *e_in, double *w_ou
     }
     EE_CUDA(cudaMemsetAsync(Q, 0, qbytes, st));
     // small device arrays
-    double *dd = (double *)dev_alloc(sizeof(double) * n * 8);
+    double *dd = (double *)dev_alloc(sizeof(double) * n * 9);
     double *d_d = dd, *d_e = dd + n, *d_z = dd + 2 * n, *d_dl = dd + 3 * n, *d_w = dd + 4 * n, *d_tau = dd + 5 * n,
-           *d_lam = dd + 6 * n, *d_zt = dd + 7 * n;
+           *d_lam = dd + 6 * n, *d_zt = dd + 7 * n, *d_e2 = dd + 8 * n;
     int *di = (int *)dev_alloc(sizeof(int) * n * 4);
     int *d_org = di, *d_rowperm = di + n, *d_map = di + 2 * n, *d_ord = di + 3 * n;
     Rot *d_rot = (Rot *)dev_alloc(sizeof(Rot) * (n + 1));
     LeafDesc *d_leaves = (LeafDesc *)dev_alloc(sizeof(LeafDesc) * leaves.size());
     EE_CUDA(cudaMemcpyAsync(d_d, hd.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
     EE_CUDA(cudaMemcpyAsync(d_e, he.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    if (penta) EE_CUDA(cudaMemcpyAsync(d_e2, he2.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
     EE_CUDA(cudaMemcpyAsync(d_leaves, leaves.data(), sizeof(LeafDesc) * leaves.size(), cudaMemcpyHostToDevice, st));
 
     // ---- leaves ------------------------------------------------------------------------------
-    leaf_jacobi_kernel<<<(unsigned)leaves.size(), 32, 0, st>>>(d_leaves, d_d, d_e, Q, ldq, d_lam);
+    leaf_jacobi_kernel<<<(unsigned)leaves.size(), 32, 0, st>>>(d_leaves, d_d, d_e, penta ? d_e2 : nullptr, Q, ldq, d_lam);
     EE_CHECK_LAUNCH();
     std::vector<double> D(n);  // eigenvalues in physical column order
     EE_CUDA(cudaMemcpyAsync(D.data(), d_lam, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
@@ -407,22 +455,22 @@ int dc_dev(int n, int nvec, const double *d_in, const double *e_in, double *w_ou
     double t_defl = 0, t_perm = 0, t_sec = 0, t_gemm = 0, t_sort = 0;
     auto wall = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     // ---- merges (post-order) -----------------------------------------------------------------
-    for (const Node &m : merges) {
+    // one rank-one update  diag(D) + rho z z^T  of the node [m.lo, m.hi), z = Q_node^T w / sqrt(2) (w given by
+    // zs, |w|^2 = 2).  blockdiag: the node's eigenvector matrix is still diag(Q1, Q2) and ord holds the two
+    // children's orders; otherwise it is dense and ord holds the node's own order.
+    auto rank_one_update = [&](const Node &m, double rho, const ZSpec &zs, bool blockdiag) {
         const int lo = m.lo, n1 = m.mid - m.lo, ns = m.hi - m.lo, n2 = ns - n1;
         double *Qb = Q + (long long)lo * ldq + lo, *Q2b = Q2 + (long long)lo * ldq + lo;
         double *Dn = D.data() + lo;
         double tw0 = wall();
-        gather_z_kernel<<<(ns + 255) / 256, 256, 0, st>>>(Q, ldq, lo, n1, ns, d_z);
+        gather_z_kernel<<<(ns + 255) / 256, 256, 0, st>>>(Q, ldq, lo, ns, zs, d_z);
         EE_CHECK_LAUNCH();
         EE_CUDA(cudaMemcpyAsync(hz.data(), d_z, sizeof(double) * ns, cudaMemcpyDeviceToHost, st));
         EE_CUDA(cudaStreamSynchronize(st));
-        double rho = he[m.mid];
-        if (rho < 0.0) for (int j = n1; j < ns; j++) hz[j] = -hz[j];
         const double isq2 = 1.0 / sqrt(2.0);
         for (int j = 0; j < ns; j++) hz[j] *= isq2;
-        rho = fabs(2.0 * rho);
-        // ascending order over both children (merge of the two sorted index lists)
-        {
+        if (blockdiag) {
+            // ascending order over both children (merge of the two sorted index lists)
             int a = 0, b = 0, t = 0;
             const int *oa = ord.data() + lo, *ob = ord.data() + lo + n1;
             while (a < n1 && b < n2) {
@@ -430,17 +478,19 @@ int dc_dev(int n, int nvec, const double *d_in, const double *e_in, double *w_ou
             }
             while (a < n1) idx[t++] = oa[a++];
             while (b < n2) idx[t++] = n1 + ob[b++];
+        } else {
+            for (int t = 0; t < ns; t++) idx[t] = ord[lo + t];
         }
         double dmax = 0.0, zmax = 0.0;
         for (int j = 0; j < ns; j++) { dmax = fmax(dmax, fabs(Dn[j])); zmax = fmax(zmax, fabs(hz[j])); }
         const double tol = 8.0 * HALF_EPS * fmax(dmax, zmax);
         if (rho * zmax <= tol) {
             for (int t = 0; t < ns; t++) ord[lo + t] = idx[t];
-            continue;
+            return;
         }
         // ---- deflation (dlaed2 logic) ---------------------------------------------------
         nondefl.clear(); defl.clear(); rots.clear();
-        for (int j = 0; j < ns; j++) coltype[j] = (j < n1) ? 1 : 3;
+        for (int j = 0; j < ns; j++) coltype[j] = !blockdiag ? 2 : (j < n1) ? 1 : 3;
         int pj = -1;
         for (int t = 0; t < ns; t++) {
             const int nj = idx[t];
@@ -558,6 +608,37 @@ int dc_dev(int n, int nvec, const double *d_in, const double *e_in, double *w_ou
             for (int j = 0; j < ns; j++) ord[lo + j] = neword[j];
         }
         t_sort += wall() - tw1;
+    };
+    const double SQ2 = sqrt(2.0);
+    (void)SQ2;
+    for (size_t t = 0; t < merges.size(); t++) {
+        const Node &m = merges[t];
+        const Tear &tr = tears[t];
+        bool blockdiag = true;
+        if (tr.sig1 > 0.0) {
+            ZSpec zs = {{m.mid - 2, m.mid - 1, m.mid, m.mid}, {tr.x0, tr.x1, 1.0, 0.0}};
+            if (tr.x0 == 0.0) zs.row[0] = m.mid - 1;   // tridiagonal split next to the block edge: never read
+            rank_one_update(m, 2.0 * tr.sig1, zs, true);
+            blockdiag = false;
+        }
+        if (tr.sig2 > 0.0) {
+            ZSpec zs = {{m.mid - 1, m.mid + 1, m.mid, m.mid}, {tr.s2, 1.0, 0.0, 0.0}};
+            rank_one_update(m, 2.0 * tr.sig2, zs, blockdiag);
+            blockdiag = false;
+        }
+        if (blockdiag) {
+            // no coupling at all: the node's order is the merge of the children's orders
+            const int lo = m.lo, n1 = m.mid - m.lo, ns = m.hi - m.lo, n2 = ns - n1;
+            const double *Dn = D.data() + lo;
+            int a = 0, b = 0, q = 0;
+            const int *oa = ord.data() + lo, *ob = ord.data() + lo + n1;
+            while (a < n1 && b < n2) {
+                if (Dn[oa[a]] <= Dn[n1 + ob[b]]) idx[q++] = oa[a++]; else idx[q++] = n1 + ob[b++];
+            }
+            while (a < n1) idx[q++] = oa[a++];
+            while (b < n2) idx[q++] = n1 + ob[b++];
+            for (int j = 0; j < ns; j++) ord[lo + j] = idx[j];
+        }
     }
     for (auto &e : evs) cudaEventDestroy(e);
     c.timings[17] = t_defl; c.timings[18] = t_perm; c.timings[19] = t_sec; c.timings[20] = t_gemm; c.timings[21] = t_sort;

@@ -24,16 +24,18 @@ constexpr int TB = 128;       // diagonal block handled by one tinv CTA
 constexpr int KSPLIT = 64;
 constexpr int SS_SPLIT_MAX = 6;
 
-// V(g, c) = u_{i0+c}(g) for g < i0+c, from the local cyclic pieces of a (zero elsewhere)
+// V(g, c) = u_{i0+c}(g) for g < i0+c-(iblk-1), from the local cyclic pieces of a (zero elsewhere).
+// iblk = 1: reflectors of eigen_trd (column gc has gc rows); iblk = 2: of eigen_prd (gc-1 rows),
+// the nb argument of eigen_common_trbakwy (src/trbakwy4.F:77, src/eigen_sx.F:245-247).
 __global__ void gather_v_kernel(const double *A, int lda, int px, int py, int x, int y, int i0, int mb, int rows,
-                                double *V, int ldv)
+                                int iblk, double *V, int ldv)
 {
     const int c = blockIdx.y;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= ldv) return;
     const int gc = i0 + c;
     double v = 0.0;
-    if (c < mb && g < gc && g < rows && (gc % py) == y && (g % px) == x) v = A[(size_t)(gc / py) * lda + g / px];
+    if (c < mb && g < gc - (iblk - 1) && g < rows && (gc % py) == y && (g % px) == x) v = A[(size_t)(gc / py) * lda + g / px];
     V[(size_t)c * ldv + g] = v;
 }
 
@@ -115,19 +117,20 @@ int choose_ksplit(long long tiles, int K, int slots)
 
 }  // namespace
 
-void trbak_dev(int n, int nvec, const double *a, int lda, double *z, int ldz, const double *e, int m_backward)
+void trbak_dev(int n, int nvec, const double *a, int lda, double *z, int ldz, const double *e, int m_backward, int iblk)
 {
     (void)e;
+    if (iblk < 1) iblk = 1;
     Context &c = ctx();
     const Grid &g = c.g;
     cudaStream_t st = c.stream;
-    if (n <= 1 || nvec <= 0) return;
+    if (n <= iblk || nvec <= 0) return;
     // m_backward is a blocking hint (reference default 128, cap nsm = 256).  The two GEMMs per
     // block run at K = mb resp. M = mb; wide blocks keep the C read-modify-write of Z hidden.
     int mb = m_backward < MB_MAX ? m_backward : MB_MAX;
     if (n >= 8192 && mb < MB_MAX) mb = MB_MAX;
     if (mb < 1) mb = 1;
-    if (mb > n - 1) mb = n - 1;
+    if (mb > n - iblk) mb = n - iblk;
     const int nvl = cyc_count(nvec, g.py, g.y);
     const bool multi = g.nnod > 1;
     const int ldv = (n + 15) & ~15;
@@ -160,18 +163,18 @@ void trbak_dev(int n, int nvec, const double *a, int lda, double *z, int ldz, co
             float ms; EE_CUDA(cudaEventElapsedTime(&ms, pe0, pe1)); tcls[cls] += ms * 1e-3;
         }
     };
-    // reflector columns i = 1..n-1 ; first block takes the remainder (trbakwy4.F:292)
-    int i0 = 1;
-    int first = (n - 1) % mb;
+    // reflector columns i = iblk..n-1 ; first block takes the remainder (trbakwy4.F:292)
+    int i0 = iblk;
+    int first = (n - iblk) % mb;
     while (i0 <= n - 1) {
-        const int cur = (i0 == 1 && first != 0) ? first : mb;
-        const int rows = i0 + cur - 1;  // longest reflector of the block
+        const int cur = (i0 == iblk && first != 0) ? first : mb;
+        const int rows = i0 + cur - iblk;  // longest reflector of the block
         const int nrl = cyc_count(rows, g.px, g.x);
         // ---- V panel (K15) ---------------------------------------------------------------
         pb();
         {
             dim3 grid((ldv + 255) / 256, cur);
-            gather_v_kernel<<<grid, 256, 0, st>>>(a, lda, g.px, g.py, g.x, g.y, i0, cur, rows, V, ldv);
+            gather_v_kernel<<<grid, 256, 0, st>>>(a, lda, g.px, g.py, g.x, g.y, i0, cur, rows, iblk, V, ldv);
             EE_CHECK_LAUNCH();
             if (multi) comm_allreduce_sum(V, (size_t)ldv * cur, COMM_WORLD, st);
             if (g.px > 1) {

@@ -104,19 +104,31 @@ __device__ __forceinline__ double block_sum(double v, double *sm)
 // ---------------------------------------------------------------------------------------
 // SYMV over the local strict upper staircase + panel dot products
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void symv_strip(const TrdP &P, int br, int sc, int nclL, double *smem)
+// NV = 1: one vector (eigen_trd_au).  NV = 2: the two reflectors of a column pair in ONE pass
+// over the matrix (eigen_prd_au, src/eigen_prd_t2.F:153-206): half the bytes per column.
+template <int NV>
+struct SymvIO {
+    const double *u[NV];     // replicated input vectors (entries >= P.L are ignored)
+    double *prow[NV];        // row partials  [strip][row]
+    double *pcol[NV];        // col partials  [tile row][col]
+};
+
+template <int NV>
+__device__ __forceinline__ void symv_strip(const TrdP &P, const SymvIO<NV> &io, int br, int sc, int nclL, double *smem)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r0 = br * TR;
-    const double *__restrict__ u = P.ucur;
     // this thread's 4 rows
     int rloc[4] = {r0 + 2 * lane, r0 + 2 * lane + 1, r0 + 64 + 2 * lane, r0 + 64 + 2 * lane + 1};
-    double ux[4], acc_row[4];
+    double ux[NV][4], acc_row[NV][4];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         long long g = (long long)rloc[q] * P.px + P.x;
-        ux[q] = (g < P.L) ? __ldg(u + g) : 0.0;
-        acc_row[q] = 0.0;
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            ux[v][q] = (g < P.L) ? __ldg(io.u[v] + g) : 0.0;
+            acc_row[v][q] = 0.0;
+        }
     }
     const long long rmax_g = (long long)(r0 + TR - 1) * P.px + P.x;
     for (int st = 0; st < P.sw; st++) {
@@ -131,12 +143,6 @@ __device__ __forceinline__ void symv_strip(const TrdP &P, int br, int sc, int nc
         for (int c = 0; c < 8; c++) {
             v0[c] = __ldcs(reinterpret_cast<const double2 *>(base + (size_t)c * P.lda));
             v1[c] = __ldcs(reinterpret_cast<const double2 *>(base + (size_t)c * P.lda + 64));
-        }
-        double uy[8];
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-            long long g = (long long)(cw + c) * P.py + P.y;
-            uy[c] = (g < P.L) ? __ldg(u + g) : 0.0;
         }
         const long long cmin_g = (long long)c0 * P.py + P.y;
         const long long cmax_g = (long long)(c0 + TC - 1) * P.py + P.y;
@@ -155,21 +161,24 @@ __device__ __forceinline__ void symv_strip(const TrdP &P, int br, int sc, int nc
                 if (!(cin && gr[3] < gc)) v1[c].y = 0.0;
             }
         }
-        double acc_col[8];
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
-            acc_row[0] = fma(v0[c].x, uy[c], acc_row[0]);
-            acc_row[1] = fma(v0[c].y, uy[c], acc_row[1]);
-            acc_row[2] = fma(v1[c].x, uy[c], acc_row[2]);
-            acc_row[3] = fma(v1[c].y, uy[c], acc_row[3]);
-            double s = v0[c].x * ux[0];
-            s = fma(v0[c].y, ux[1], s);
-            s = fma(v1[c].x, ux[2], s);
-            s = fma(v1[c].y, ux[3], s);
-            acc_col[c] = s;
-        }
-        // reduce-scatter the 8 column sums over the 32 lanes (9 exchanges instead of 40)
-        {
+        for (int v = 0; v < NV; v++) {
+            double acc_col[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const long long g = (long long)(cw + c) * P.py + P.y;
+                const double uy = (g < P.L) ? __ldg(io.u[v] + g) : 0.0;
+                acc_row[v][0] = fma(v0[c].x, uy, acc_row[v][0]);
+                acc_row[v][1] = fma(v0[c].y, uy, acc_row[v][1]);
+                acc_row[v][2] = fma(v1[c].x, uy, acc_row[v][2]);
+                acc_row[v][3] = fma(v1[c].y, uy, acc_row[v][3]);
+                double s = v0[c].x * ux[v][0];
+                s = fma(v0[c].y, ux[v][1], s);
+                s = fma(v1[c].x, ux[v][2], s);
+                s = fma(v1[c].y, ux[v][3], s);
+                acc_col[c] = s;
+            }
+            // reduce-scatter the 8 column sums over the 32 lanes (9 exchanges instead of 40)
             const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
             double h[4];
 #pragma unroll
@@ -192,28 +201,33 @@ __device__ __forceinline__ void symv_strip(const TrdP &P, int br, int sc, int nc
             r += __shfl_xor_sync(0xffffffffu, r, 1);
             if ((lane & 3) == 0) {
                 int c = (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0);
-                P.Pcol[(size_t)br * P.ldpcol + cw + c] = r;
+                io.pcol[v][(size_t)br * P.ldpcol + cw + c] = r;
             }
         }
     }
     // cross-warp reduction of the row sums
     double *sm = smem;  // [8][TR]
-    __syncthreads();
-    sm[warp * TR + 2 * lane] = acc_row[0];
-    sm[warp * TR + 2 * lane + 1] = acc_row[1];
-    sm[warp * TR + 64 + 2 * lane] = acc_row[2];
-    sm[warp * TR + 64 + 2 * lane + 1] = acc_row[3];
-    __syncthreads();
-    if (threadIdx.x < TR) {
-        double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < 8; w++) s += sm[w * TR + threadIdx.x];
-        P.Prow[(size_t)sc * P.ldprow + r0 + threadIdx.x] = s;
+    for (int v = 0; v < NV; v++) {
+        __syncthreads();
+        sm[warp * TR + 2 * lane] = acc_row[v][0];
+        sm[warp * TR + 2 * lane + 1] = acc_row[v][1];
+        sm[warp * TR + 64 + 2 * lane] = acc_row[v][2];
+        sm[warp * TR + 64 + 2 * lane + 1] = acc_row[v][3];
+        __syncthreads();
+        if (threadIdx.x < TR) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) s += sm[w * TR + threadIdx.x];
+            io.prow[v][(size_t)sc * P.ldprow + r0 + threadIdx.x] = s;
+        }
     }
 }
 
-// chunk of the panel dot products  s_l = V_l^T u, t_l = U_l^T u  (finished slots k+1..m0-1)
-__device__ void dots_chunk(const TrdP &P, int ch, double *smem)
+// chunk of the panel dot products  s_l = V_l^T u, t_l = U_l^T u  (finished slots first..first+nd-1)
+// for NV vectors; results st[v*2*MAXM + (0..nd-1 | nd..2nd-1)]
+template <int NV>
+__device__ void dots_chunk(const TrdP &P, const double *const *uvec, int first_slot, int ch)
 {
     const int nd = P.ndone;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // 8 warps
@@ -221,12 +235,21 @@ __device__ void dots_chunk(const TrdP &P, int ch, double *smem)
     const int j0 = ch * rows_per, j1 = min(P.L, j0 + rows_per);
     // each warp takes columns l = warp, warp+8, ... of the 2*nd vectors
     for (int c = warp; c < 2 * nd; c += 8) {
-        const double *col = (c < nd) ? (P.V + (size_t)(P.k + 1 + c) * P.npad)
-                                     : (P.U + (size_t)(P.k + 1 + c - nd) * P.npad);
-        double s = 0.0;
-        for (int j = j0 + lane; j < j1; j += 32) s = fma(__ldg(col + j), __ldg(P.ucur + j), s);
-        s = warp_sum(s);
-        if (lane == 0) P.dots_part[(size_t)ch * 2 * MAXM + c] = s;
+        const double *col = (c < nd) ? (P.V + (size_t)(first_slot + c) * P.npad)
+                                     : (P.U + (size_t)(first_slot + c - nd) * P.npad);
+        double s[NV];
+#pragma unroll
+        for (int v = 0; v < NV; v++) s[v] = 0.0;
+        for (int j = j0 + lane; j < j1; j += 32) {
+            const double cj = __ldg(col + j);
+#pragma unroll
+            for (int v = 0; v < NV; v++) s[v] = fma(cj, __ldg(uvec[v] + j), s[v]);
+        }
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            double t = warp_sum(s[v]);
+            if (lane == 0) P.dots_part[((size_t)ch * NV + v) * 2 * MAXM + c] = t;
+        }
     }
     // last chunk CTA reduces the partials in fixed order
     __shared__ unsigned int s_last;
@@ -236,14 +259,27 @@ __device__ void dots_chunk(const TrdP &P, int ch, double *smem)
     __syncthreads();
     if (s_last == NCH - 1) {
         __threadfence();
-        for (int c = threadIdx.x; c < 2 * nd; c += blockDim.x) {
-            double s = 0.0;
-            for (int q = 0; q < NCH; q++) s += __ldcg(P.dots_part + (size_t)q * 2 * MAXM + c);
-            P.st[c] = s;
+        for (int c = threadIdx.x; c < 2 * nd * NV; c += blockDim.x) {
+            const int v = c / (2 * nd), cc = c - v * 2 * nd;
+            double t = 0.0;
+            for (int q = 0; q < NCH; q++) t += __ldcg(P.dots_part + ((size_t)q * NV + v) * 2 * MAXM + cc);
+            P.st[(size_t)v * 2 * MAXM + cc] = t;
         }
         if (threadIdx.x == 0) P.tickets[0] = 0u;
     }
-    (void)smem;
+}
+
+// fold the triangle: CTA column bx sweeps strip (nsc-1-bx) and then strip bx, so that no CTA is empty
+__device__ __forceinline__ bool fold_triangle(const TrdP &P, int bid, int gx, int nclL, int &sc, int &br)
+{
+    const int nsc = nstrips_of(P, nclL);
+    const int bx = bid % gx, by = bid / gx;
+    const int sc1 = nsc - 1 - bx, sc2 = bx;
+    const int n1 = strip_rows(P, sc1, nclL);
+    if (by < n1) { sc = sc1; br = by; return true; }
+    if (sc2 == sc1) return false;
+    br = by - n1; sc = sc2;
+    return br < strip_rows(P, sc2, nclL);
 }
 
 __global__ void __launch_bounds__(256, 2) symv_kernel(TrdP P, int gx, int ntile_blocks)
@@ -251,23 +287,16 @@ __global__ void __launch_bounds__(256, 2) symv_kernel(TrdP P, int gx, int ntile_
     __shared__ double smem[8 * TR];
     const int bid = blockIdx.x;
     if (bid >= ntile_blocks) {
-        if (P.ndone > 0) dots_chunk(P, bid - ntile_blocks, smem);
+        const double *uv[1] = {P.ucur};
+        if (P.ndone > 0) dots_chunk<1>(P, uv, P.k + 1, bid - ntile_blocks);
         return;
     }
     const int nclL = ncl_of(P);
-    const int nsc = nstrips_of(P, nclL);
-    const int bx = bid % gx, by = bid / gx;
-    // fold the triangle: pair strip (nsc-1-bx) with strip bx
-    const int sc1 = nsc - 1 - bx, sc2 = bx;
-    const int n1 = strip_rows(P, sc1, nclL);
     int sc, br;
-    if (by < n1) { sc = sc1; br = by; }
-    else {
-        if (sc2 == sc1) return;
-        br = by - n1; sc = sc2;
-        if (br >= strip_rows(P, sc2, nclL)) return;
-    }
-    symv_strip(P, br, sc, nclL, smem);
+    if (!fold_triangle(P, bid, gx, nclL, sc, br)) return;
+    SymvIO<1> io;
+    io.u[0] = P.ucur; io.prow[0] = P.Prow; io.pcol[0] = P.Pcol;
+    symv_strip<1>(P, io, br, sc, nclL, smem);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -616,6 +645,374 @@ __global__ void scale_upper_kernel(double *A, int lda, int n, int px, int py, in
     if (gr <= gc) A[(size_t)il * lda + jl] *= s;
 }
 
+// =========================================================================================
+// eigen_prd: reduction to penta-diagonal form, two columns per step
+// (reference: src/eigen_prd.F:341-580, _t4x.F:114-353 compute_u, _t2.F:153-206 au,
+//  _t6_3.F:160-458 compute_v, _t5.F local_2update, _t7.F panel load/store, _t8.F init/final).
+//
+// A column pair (a = column c2, b = column c2-1; L = c2-1 rows lie above the band) is reduced by
+// two ordinary Householder reflectors H_a (length L, pivot row L-1) and H_b (length L-1, pivot row
+// L-2) -- what the reference's Cholesky-QR + coupling matrix c produce
+// (src/eigen_prd_t4x.F:262-353: u_b = (H_a x_b)(1:L-1), e(i-1,1) = (H_a x_b)(L)).  H_a is applied
+// to column b explicitly (one dot product, no re-orthogonalisation needed), both reflectors are
+// known before the matrix is touched, so ONE pass over the local staircase yields A u_a and A u_b
+// (symv_strip<2>): 2/3 n^3 bytes instead of 4/3 n^3.  The second reflector's p is corrected
+// algebraically for the first one:
+//     v_a = (p_a - alpha_a u_a)/beta_a                 alpha_a = u_a^T p_a / (2 beta_a)
+//     p_b' = p_b - u_a (v_a^T u_b) - v_a (u_a^T u_b)
+//     v_b = (p_b' - alpha_b u_b)/beta_b                alpha_b = u_b^T p_b' / (2 beta_b)
+// (u_a, v_a), (u_b, v_b) then enter the panel exactly like two tridiagonalisation steps, so the
+// rank-2k update and the back-transformation are shared with eigen_trd.
+// One pair = four launches:  next2 (finish previous pair, form the raw pair, H_a scalars) ->
+// house2 (H_a on column b, H_b scalars) -> symv2 -> pvec2.
+// =========================================================================================
+struct PrdP : TrdP {
+    double *xa, *xb;          // current pair: raw columns, then u_a (length L), u_b (length L-1)
+    double *xa_n, *xb_n;      // next pair, written by next2_kernel
+    double *pa, *pb;          // A u_a, A u_b minus the panel corrections (pb = pa + npad)
+    double *Prow_b, *Pcol_b;  // tile partials of the second vector
+    double *e2_out;           // second off-diagonal: e2(c) = T(c-2, c)
+};
+// scal[]: 0 g_a  1 beta_a  2 u_a^T x_b  3 g_b  4 beta_b  5 u_a^T u_b  6 alpha_a  7 v_a^T u_b  8 alpha_b
+enum { S_GA = 0, S_BA = 1, S_SAB = 2, S_GB = 3, S_BB = 4, S_CAB = 5, S_ALA = 6, S_W = 7, S_ALB = 8 };
+
+// v_a(g), v_b(g) of the pair whose vectors are in xa/xb/pa/pb
+__device__ __forceinline__ void vpair(const PrdP &P, int g, double &ua, double &ub, double &va, double &vb)
+{
+    ua = P.xa[g]; ub = P.xb[g];
+    va = (P.pa[g] - P.scal[S_ALA] * ua) / P.scal[S_BA];
+    vb = (P.pb[g] - ua * P.scal[S_W] - va * P.scal[S_CAB] - P.scal[S_ALB] * ub) / P.scal[S_BB];
+}
+
+// P.k = slot of column a of the NEW pair (columns c2 = i_base + k, c1 = c2 - 1); the previous pair
+// (slots k+2, k+1) is finished here unless P.first.  P.has_next = 0: panel end, only finish.
+__global__ void __launch_bounds__(VR * VS) next2_kernel(PrdP P)
+{
+    __shared__ double s_ru[2][MAXM], s_rv[2][MAXM];   // rows c2 (0) and c1 (1) of U and V, slots lo..m0-1
+    __shared__ double s_acc[2][VS][VR];
+    __shared__ double s_red[VR * VS / 32];
+    __shared__ unsigned int s_last;
+    const int k = P.k;
+    const int c2 = P.i_base + k, c1 = c2 - 1, L = c2 - 1;
+    const int Lp = L + 2;                 // reflector length of the previous pair's column a
+    const int lo = k + 1, nl = P.m0 - lo; // finished slots
+    if (P.has_next) {
+        for (int l = threadIdx.x; l < nl; l += blockDim.x) {
+            const int slot = lo + l;
+            double u2, v2, u1, v1;
+            if (!P.first && slot <= k + 2) {
+                double ua, ub, va, vb;
+                vpair(P, c2, ua, ub, va, vb);
+                u2 = (slot == k + 2) ? ua : ub; v2 = (slot == k + 2) ? va : vb;
+                vpair(P, c1, ua, ub, va, vb);
+                u1 = (slot == k + 2) ? ua : ub; v1 = (slot == k + 2) ? va : vb;
+            } else {
+                u2 = P.U[(size_t)slot * P.npad + c2]; v2 = P.V[(size_t)slot * P.npad + c2];
+                u1 = P.U[(size_t)slot * P.npad + c1]; v1 = P.V[(size_t)slot * P.npad + c1];
+            }
+            s_ru[0][l] = u2; s_rv[0][l] = v2; s_ru[1][l] = u1; s_rv[1][l] = v1;
+        }
+    }
+    __syncthreads();
+    const int r = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int g = blockIdx.x * VR + r;
+    double ua = 0.0, ub = 0.0, va = 0.0, vb = 0.0;
+    if (!P.first && g < Lp) {
+        vpair(P, g, ua, ub, va, vb);
+        if (sl == 0) {
+            P.U[(size_t)(k + 2) * P.npad + g] = ua; P.V[(size_t)(k + 2) * P.npad + g] = va;
+            P.U[(size_t)(k + 1) * P.npad + g] = ub; P.V[(size_t)(k + 1) * P.npad + g] = vb;
+        }
+    }
+    if (!P.has_next) return;
+    double acc_a = 0.0, acc_b = 0.0;
+    if (g <= c2) {
+        if (sl == 0) {
+            acc_a = P.W[(size_t)k * P.npad + g];
+            if (g <= c1) acc_b = P.W[(size_t)(k - 1) * P.npad + g];
+        }
+        for (int l = sl; l < nl; l += VS) {
+            const int slot = lo + l;
+            double uj, vj;
+            if (!P.first && slot == k + 2) { uj = ua; vj = va; }
+            else if (!P.first && slot == k + 1) { uj = ub; vj = vb; }
+            else { uj = __ldg(P.U + (size_t)slot * P.npad + g); vj = __ldg(P.V + (size_t)slot * P.npad + g); }
+            acc_a = fma(-uj, s_rv[0][l], acc_a); acc_a = fma(-vj, s_ru[0][l], acc_a);
+            acc_b = fma(-uj, s_rv[1][l], acc_b); acc_b = fma(-vj, s_ru[1][l], acc_b);
+        }
+    }
+    s_acc[0][sl][r] = acc_a; s_acc[1][sl][r] = acc_b;
+    __syncthreads();
+    double n22 = 0.0, n12 = 0.0;
+    if (sl == 0) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int q = 0; q < VS; q++) { a += s_acc[0][q][r]; b += s_acc[1][q][r]; }
+        if (g <= c2) {
+            P.xa_n[g] = a;
+            P.xb_n[g] = (g <= c1) ? b : 0.0;
+            if (g < L) { n22 = a * a; n12 = a * b; }
+        }
+        n22 = warp_sum(n22); n12 = warp_sum(n12);
+    }
+    if (threadIdx.x == 0) {
+        P.part[blockIdx.x] = n22; P.part[gridDim.x + blockIdx.x] = n12;
+        __threadfence();
+        s_last = atomicAdd(&P.tickets[2], 1u);
+    }
+    __syncthreads();
+    if (s_last == gridDim.x - 1) {
+        __threadfence();
+        double s0 = 0.0, s1 = 0.0;
+        for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) { s0 += __ldcg(P.part + q); s1 += __ldcg(P.part + gridDim.x + q); }
+        const double t22 = block_sum<VR * VS>(s0, s_red);
+        const double t12 = block_sum<VR * VS>(s1, s_red);
+        if (threadIdx.x == 0) {
+            // Householder scalars of column a (src/eigen_prd_t4x.F:262-275; sigma = 0 -> g = 0, beta = 1)
+            const double a_piv = __ldcg(P.xa_n + L - 1);
+            double g_a, u_piv, beta;
+            if (t22 != 0.0) { g_a = -copysign(sqrt(t22), a_piv); u_piv = a_piv - g_a; beta = -u_piv * g_a; }
+            else { g_a = 0.0; u_piv = 0.0; beta = 1.0; }
+            P.scal[S_GA] = g_a; P.scal[S_BA] = beta;
+            P.scal[S_SAB] = t12 - g_a * __ldcg(P.xb_n + L - 1);     // u_a^T x_b
+            P.xa_n[L - 1] = u_piv;
+            P.d_out[c2] = __ldcg(P.xa_n + c2);       // T(c2,c2)
+            P.e_out[c2] = __ldcg(P.xa_n + c2 - 1);   // T(c2-1,c2)     (e(i,1) = u_t(8), prd_t4x.F:329)
+            P.d_out[c1] = __ldcg(P.xb_n + c1);
+            P.e2_out[c2] = g_a;                      // T(c2-2,c2)     (e(i,2) = sgm(2))
+            P.tickets[2] = 0u;
+        }
+    }
+}
+
+// x_b <- H_a x_b on rows < L ; scalars of H_b (pivot row L-2) ; u_a^T u_b
+__global__ void __launch_bounds__(256) house2_kernel(PrdP P)
+{
+    __shared__ double s_red[8];
+    __shared__ unsigned int s_last;
+    const int c2 = P.i_base + P.k, c1 = c2 - 1, L = c2 - 1;
+    const double coef = P.scal[S_SAB] / P.scal[S_BA];
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    double n11 = 0.0, cd = 0.0;
+    if (g < L) {
+        const double ua = P.xa[g];
+        const double b = P.xb[g] - ua * coef;
+        P.xb[g] = b;
+        if (g < L - 1) { n11 = b * b; cd = ua * b; }
+    }
+    n11 = block_sum<256>(n11, s_red);
+    cd = block_sum<256>(cd, s_red);
+    if (threadIdx.x == 0) {
+        P.part[blockIdx.x] = n11; P.part[gridDim.x + blockIdx.x] = cd;
+        __threadfence();
+        s_last = atomicAdd(&P.tickets[1], 1u);
+    }
+    __syncthreads();
+    if (s_last == gridDim.x - 1) {
+        __threadfence();
+        double s0 = 0.0, s1 = 0.0;
+        for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) { s0 += __ldcg(P.part + q); s1 += __ldcg(P.part + gridDim.x + q); }
+        const double t11 = block_sum<256>(s0, s_red);
+        const double tcd = block_sum<256>(s1, s_red);
+        if (threadIdx.x == 0) {
+            const double b_piv = __ldcg(P.xb + L - 2);
+            double g_b, u_piv, beta;
+            if (t11 != 0.0) { g_b = -copysign(sqrt(t11), b_piv); u_piv = b_piv - g_b; beta = -u_piv * g_b; }
+            else { g_b = 0.0; u_piv = 0.0; beta = 1.0; }
+            P.scal[S_GB] = g_b; P.scal[S_BB] = beta;
+            P.scal[S_CAB] = tcd - g_b * __ldcg(P.xa + L - 2);
+            P.e2_out[c1] = g_b;                       // T(c1-2,c1)    (e(i-1,2) = sgm(1))
+            P.e_out[c1] = __ldcg(P.xb + L - 1);       // T(c1-1,c1) = (H_a x_b)(L-1)   (e(i-1,1) = sgm(2) r12)
+            P.xb[L - 2] = u_piv;
+            P.xb[L - 1] = 0.0;
+            P.tickets[1] = 0u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 2) symv2_kernel(PrdP P, int gx, int ntile_blocks)
+{
+    __shared__ double smem[8 * TR];
+    const int bid = blockIdx.x;
+    if (bid >= ntile_blocks) {
+        const double *uv[2] = {P.xa, P.xb};
+        if (P.ndone > 0) dots_chunk<2>(P, uv, P.k + 1, bid - ntile_blocks);
+        return;
+    }
+    const int nclL = ncl_of(P);
+    int sc, br;
+    if (!fold_triangle(P, bid, gx, nclL, sc, br)) return;
+    SymvIO<2> io;
+    io.u[0] = P.xa; io.prow[0] = P.Prow; io.pcol[0] = P.Pcol;
+    io.u[1] = P.xb; io.prow[1] = P.Prow_b; io.pcol[1] = P.Pcol_b;
+    symv_strip<2>(P, io, br, sc, nclL, smem);
+}
+
+// p_a, p_b from the tile partials minus the panel corrections; u_a^T p_a, u_b^T p_a, u_b^T p_b;
+// last CTA: alpha_a, v_a^T u_b, alpha_b.  MODE as pvec_kernel.
+template <int MODE>
+__global__ void __launch_bounds__(VR * VS) pvec2_kernel(PrdP P, PeerView pv, unsigned long long epoch)
+{
+    __shared__ double s_st[2][2 * MAXM];
+    __shared__ int s_nbr[1024];
+    __shared__ double s_acc[2][VS][VR];
+    __shared__ double s_red[VR * VS / 32];
+    __shared__ unsigned int s_last;
+    const int nd = P.ndone;
+    const int nclL = ncl_of(P);
+    const int nsc = nstrips_of(P, nclL);
+    constexpr bool PARTIAL = (MODE == 0 || MODE == 1 || MODE == 3);
+    constexpr bool FINISH = (MODE == 0 || MODE == 2 || MODE == 4);
+    const int par = (int)(epoch & 1ull);
+    if (MODE == 4 && threadIdx.x == 0) {
+        const volatile unsigned long long *fl = pv.flags[pv.r] + (size_t)par * pv.P;
+        for (int q = 0; q < pv.P; q++) {
+            unsigned long long spins = 0;
+            while (fl[q] < epoch) {
+                __nanosleep(64);
+                if (++spins > (1ull << 27)) { *pv.err = 1; break; }
+            }
+        }
+        __threadfence_system();
+    }
+    if (PARTIAL) {
+        for (int s = threadIdx.x; s < nsc; s += blockDim.x) s_nbr[s] = strip_rows(P, s, nclL);
+    }
+    if (FINISH) {
+        for (int c = threadIdx.x; c < 2 * nd; c += blockDim.x) { s_st[0][c] = P.st[c]; s_st[1][c] = P.st[2 * MAXM + c]; }
+    }
+    __syncthreads();
+    const int r = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int g = blockIdx.x * VR + r;
+    const int first_slot = P.k + 1;
+    double acc_a = 0.0, acc_b = 0.0;
+    if (g < P.L) {
+        if (PARTIAL) {
+            const bool rown = (g % P.px) == P.x, coln = (g % P.py) == P.y;
+            if (rown) {
+                const int jl = g / P.px, br = jl / TR;
+                for (int s = nsc - 1 - sl; s >= 0 && s_nbr[s] > br; s -= VS) {
+                    acc_a += __ldcs(P.Prow + (size_t)s * P.ldprow + jl);
+                    acc_b += __ldcs(P.Prow_b + (size_t)s * P.ldprow + jl);
+                }
+            }
+            if (coln) {
+                const int il = g / P.py;
+                const int nb = ntile_rows(P, il / TC, nclL);
+                for (int b = sl; b < nb; b += VS) {
+                    acc_a += __ldcs(P.Pcol + (size_t)b * P.ldpcol + il);
+                    acc_b += __ldcs(P.Pcol_b + (size_t)b * P.ldpcol + il);
+                }
+                if (rown && sl == 0) {
+                    const double dg = P.A[(size_t)il * P.lda + g / P.px];
+                    acc_a = fma(dg, P.xa[g], acc_a); acc_b = fma(dg, P.xb[g], acc_b);
+                }
+            }
+        } else if (sl == 0) {
+            if (MODE == 4) {
+                const double *base = pv.slots[pv.r] + (size_t)par * pv.P * pv.slot_doubles + g;
+                for (int q = 0; q < pv.P; q++) {
+                    acc_a += __ldcg(base + (size_t)q * pv.slot_doubles);
+                    acc_b += __ldcg(base + (size_t)q * pv.slot_doubles + P.npad);
+                }
+            } else { acc_a = P.pa[g]; acc_b = P.pb[g]; }
+        }
+        if (FINISH) {
+            for (int l = sl; l < nd; l += VS) {
+                const size_t off = (size_t)(first_slot + l) * P.npad + g;
+                const double ul = __ldg(P.U + off), vl = __ldg(P.V + off);
+                acc_a = fma(-ul, s_st[0][l], acc_a); acc_a = fma(-vl, s_st[0][nd + l], acc_a);
+                acc_b = fma(-ul, s_st[1][l], acc_b); acc_b = fma(-vl, s_st[1][nd + l], acc_b);
+            }
+        }
+    }
+    s_acc[0][sl][r] = acc_a; s_acc[1][sl][r] = acc_b;
+    __syncthreads();
+    double daa = 0.0, dba = 0.0, dbb = 0.0;
+    if (sl == 0) {
+        double p_a = 0.0, p_b = 0.0;
+#pragma unroll
+        for (int q = 0; q < VS; q++) { p_a += s_acc[0][q][r]; p_b += s_acc[1][q][r]; }
+        if (g < P.L) {
+            if (MODE == 3) {
+                const size_t off = ((size_t)par * pv.P + pv.r) * pv.slot_doubles + g;
+                for (int q = 0; q < pv.P; q++) { pv.slots[q][off] = p_a; pv.slots[q][off + P.npad] = p_b; }
+            } else { P.pa[g] = p_a; P.pb[g] = p_b; }
+            if (FINISH) {
+                const double ua = P.xa[g], ub = P.xb[g];
+                daa = ua * p_a; dba = ub * p_a; dbb = ub * p_b;
+            }
+        }
+        daa = warp_sum(daa); dba = warp_sum(dba); dbb = warp_sum(dbb);
+    }
+    if (MODE == 1) return;
+    if (MODE == 3) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(&P.tickets[3], 1u);
+        __syncthreads();
+        if (s_last == gridDim.x - 1 && threadIdx.x == 0) {
+            __threadfence_system();
+            for (int q = 0; q < pv.P; q++) {
+                volatile unsigned long long *fl = pv.flags[q] + (size_t)par * pv.P + pv.r;
+                *fl = epoch;
+            }
+            P.tickets[3] = 0u;
+        }
+        return;
+    }
+    if (threadIdx.x == 0) {
+        P.part[blockIdx.x] = daa; P.part[gridDim.x + blockIdx.x] = dba; P.part[2 * gridDim.x + blockIdx.x] = dbb;
+        __threadfence();
+        s_last = atomicAdd(&P.tickets[1], 1u);
+    }
+    __syncthreads();
+    if (s_last == gridDim.x - 1) {
+        __threadfence();
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) {
+            s0 += __ldcg(P.part + q); s1 += __ldcg(P.part + gridDim.x + q); s2 += __ldcg(P.part + 2 * gridDim.x + q);
+        }
+        const double taa = block_sum<VR * VS>(s0, s_red);
+        const double tba = block_sum<VR * VS>(s1, s_red);
+        const double tbb = block_sum<VR * VS>(s2, s_red);
+        if (threadIdx.x == 0) {
+            const double beta_a = P.scal[S_BA], beta_b = P.scal[S_BB], cab = P.scal[S_CAB];
+            const double alpha_a = taa / (2.0 * beta_a);
+            const double w = (tba - alpha_a * cab) / beta_a;          // v_a^T u_b
+            const double alpha_b = (tbb - 2.0 * cab * w) / (2.0 * beta_b);
+            P.scal[S_ALA] = alpha_a; P.scal[S_W] = w; P.scal[S_ALB] = alpha_b;
+            P.tickets[1] = 0u;
+        }
+    }
+}
+
+// eigen_prd_final (src/eigen_prd_t8.F:207-315): the leading nrem x nrem block holds the band entries
+// of the first columns; they are zeroed in a so that the back-transformation sees empty reflectors.
+// out[0..2] = d(0..2), out[3..4] = e1(1..2), out[5] = e2(2)   (owners only; summed by the caller)
+__global__ void prd_final_kernel(PrdP P, int nrem)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double *out = P.scal + 16;
+    for (int q = 0; q < 6; q++) out[q] = 0.0;
+    auto own = [&](int gr, int gc) { return (gr % P.px) == P.x && (gc % P.py) == P.y; };
+    auto at = [&](int gr, int gc) -> double & { return P.A[(size_t)(gc / P.py) * P.lda + gr / P.px]; };
+    for (int j = 0; j < nrem && j < P.n; j++)
+        if (own(j, j)) out[j] = at(j, j);
+    for (int j = 1; j < nrem && j < P.n; j++)
+        if (own(j - 1, j)) { out[2 + j] = at(j - 1, j); at(j - 1, j) = 0.0; }
+    if (nrem == 3 && P.n >= 3 && own(0, 2)) { out[5] = at(0, 2); at(0, 2) = 0.0; }
+}
+__global__ void prd_final_store_kernel(PrdP P, int nrem)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double *out = P.scal + 16;
+    for (int j = 0; j < nrem && j < P.n; j++) P.d_out[j] = out[j];
+    P.e_out[0] = 0.0; P.e2_out[0] = 0.0;
+    if (P.n >= 2) { P.e_out[1] = out[3]; P.e2_out[1] = 0.0; }
+    if (nrem == 3 && P.n >= 3) { P.e_out[2] = out[4]; P.e2_out[2] = out[5]; }
+}
+
 }  // namespace
 
 // =========================================================================================
@@ -921,6 +1318,220 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
         c.timings[9] = tw1 - tw0; c.timings[10] = tw2 - tw1; c.timings[11] = tw3 - tw2; c.timings[12] = tw4 - tw3;
         cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     }
+}
+
+// -----------------------------------------------------------------------------------------
+// eigen_prd driver: a (lda x ncl, local cyclic part) in/out; d, e1, e2 device arrays of length n
+// (replicated).  e1(c) = T(c-1,c), e2(c) = T(c-2,c) (0-based c).
+// -----------------------------------------------------------------------------------------
+void prd_dev(int n, double *a_user, int lda_user, double *d_out, double *e1_out, double *e2_out, int m_forward)
+{
+    Context &c = ctx();
+    const Grid &g = c.g;
+    cudaStream_t st = c.stream;
+    const int nrl = cyc_count(n, g.px, g.x), ncl = cyc_count(n, g.py, g.y);
+    EE_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * n, st));
+    EE_CUDA(cudaMemsetAsync(e1_out, 0, sizeof(double) * n, st));
+    EE_CUDA(cudaMemsetAsync(e2_out, 0, sizeof(double) * n, st));
+    const int nrem = 2 + n % 2;     // MBAND + mod(n, MBAND) leading columns are never reduced (src/eigen_prd.F:392-401)
+    int m = m_forward < n ? m_forward : n;
+    m -= m % 2;                     // the pair loop needs an even width (manual 4.4)
+    if (m < 2) m = 2;
+    if (m > MAXM) m = MAXM;
+    constexpr int WIDE_W = 128, WIDE_L = 16384;
+    const int mmax = (n > WIDE_L && m < WIDE_W) ? WIDE_W : m;
+
+    const int lda = trd_lda_pad(nrl), nclp = trd_ncl_pad(ncl);
+    double *A = (double *)dev_alloc((size_t)lda * nclp * sizeof(double));
+    EE_CUDA(cudaMemsetAsync(A, 0, (size_t)lda * nclp * sizeof(double), st));
+    if (nrl > 0 && ncl > 0)
+        EE_CUDA(cudaMemcpy2DAsync(A, (size_t)lda * sizeof(double), a_user, (size_t)lda_user * sizeof(double),
+                                  (size_t)nrl * sizeof(double), ncl, cudaMemcpyDeviceToDevice, st));
+    {
+        dim3 grid((lda + 255) / 256, nclp);
+        zero_lower_kernel<<<grid, 256, 0, st>>>(A, lda, nclp, n, g.px, g.py, g.x, g.y);
+        EE_CHECK_LAUNCH();
+    }
+    const int npad = round_up(n + 1, 256);
+    const int nstrip_max = (nclp + TC - 1) / TC;
+    const int nbr_max = lda / TR;
+    const int maxvb = (n + VR) / VR + 2;
+    size_t wsz = 0;
+    auto take = [&](size_t cnt) { size_t o = wsz; wsz += (cnt + 31) & ~(size_t)31; return o; };
+    size_t oU = take((size_t)npad * mmax), oV = take((size_t)npad * mmax), oW = take((size_t)npad * mmax);
+    size_t oX = take((size_t)4 * npad), oP = take((size_t)2 * npad);
+    size_t oProw = take((size_t)2 * nstrip_max * lda), oPcol = take((size_t)2 * nbr_max * nclp);
+    size_t oDots = take((size_t)NCH * 4 * MAXM), oSt = take(4 * MAXM), oPart = take(3 * (size_t)maxvb);
+    size_t oScal = take(32), oTick = take(32);
+    size_t oUVx = take((size_t)lda * 2 * mmax), oVUy = take((size_t)nclp * 2 * mmax);
+    double *ws = (double *)dev_alloc(wsz * sizeof(double));
+    EE_CUDA(cudaMemsetAsync(ws, 0, wsz * sizeof(double), st));
+
+    PrdP P;
+    memset(&P, 0, sizeof P);
+    P.A = A; P.lda = lda; P.px = g.px; P.py = g.py; P.x = g.x; P.y = g.y;
+    P.n = n; P.npad = npad;
+    P.U = ws + oU; P.V = ws + oV; P.W = ws + oW;
+    P.xa = ws + oX; P.xb = P.xa + npad; P.xa_n = P.xb + npad; P.xb_n = P.xa_n + npad;
+    P.pa = ws + oP; P.pb = P.pa + npad; P.pbuf = P.pa;
+    P.Prow = ws + oProw; P.Prow_b = P.Prow + (size_t)nstrip_max * lda; P.ldprow = lda;
+    P.Pcol = ws + oPcol; P.Pcol_b = P.Pcol + (size_t)nbr_max * nclp; P.ldpcol = nclp;
+    P.dots_part = ws + oDots; P.st = ws + oSt; P.part = ws + oPart; P.scal = ws + oScal;
+    P.tickets = reinterpret_cast<unsigned int *>(ws + oTick);
+    P.d_out = d_out; P.e_out = e1_out; P.e2_out = e2_out;
+    double *UVx = ws + oUVx, *VUy = ws + oVUy;
+    const bool multi = g.nnod > 1;
+    PeerView pv;
+    memset(&pv, 0, sizeof pv);
+    const bool use_peer = multi && comm_peer_setup((size_t)2 * npad, &pv);
+
+    std::vector<cudaEvent_t> pool_symv, pool_syr2k;
+    size_t pool_next = 0;
+    auto pool_get = [&]() {
+        if (pool_next == c.ev_pool.size()) { cudaEvent_t e; EE_CUDA(cudaEventCreate(&e)); c.ev_pool.push_back(e); }
+        return c.ev_pool[pool_next++];
+    };
+    auto mark = [&](int cls) {
+        if (c.profiling < 1) return;
+        cudaEvent_t e = pool_get(); EE_CUDA(cudaEventRecord(e, st));
+        (cls == 1 ? pool_symv : pool_syr2k).push_back(e);
+    };
+    c.symv_trace.clear();
+
+    int col_end = n;
+    while (col_end > nrem) {
+        int i_base;
+        if (col_end > WIDE_L && mmax > m) i_base = col_end - mmax;
+        else i_base = nrem + ((col_end - nrem - 1) / m) * m;
+        if (i_base < nrem) i_base = nrem;
+        const int m0 = col_end - i_base;   // even: n - nrem and every width are even
+        col_end = i_base;
+        P.i_base = i_base; P.m0 = m0;
+        {
+            dim3 grid((npad + 255) / 256, m0);
+            PrdP Q = P;
+            panel_load_kernel<<<grid, 256, 0, st>>>(Q, 1);
+            EE_CHECK_LAUNCH();
+            if (multi) comm_allreduce_sum(P.W, (size_t)npad * m0, COMM_WORLD, st);
+        }
+        bool stop = false;
+        for (int k = m0 - 1; k >= 1; k -= 2) {
+            const int c2 = i_base + k, L = c2 - 1;
+            if (c.debug_maxcols > 0 && (n - 1 - c2) >= c.debug_maxcols) { stop = true; break; }
+            PrdP Q = P;
+            Q.k = k; Q.L = L; Q.first = (k == m0 - 1); Q.has_next = 1; Q.ndone = m0 - 1 - k;
+            // ---- previous pair -> panel, raw pair, H_a scalars ------------------------------------
+            next2_kernel<<<(c2 + 1 + VR - 1) / VR, VR * VS, 0, st>>>(Q);
+            EE_CHECK_LAUNCH();
+            std::swap(P.xa, P.xa_n); std::swap(P.xb, P.xb_n);
+            Q.xa = P.xa; Q.xb = P.xb; Q.xa_n = P.xa_n; Q.xb_n = P.xb_n;
+            // ---- H_a on column b, H_b scalars ------------------------------------------------------
+            house2_kernel<<<(L + 255) / 256, 256, 0, st>>>(Q);
+            EE_CHECK_LAUNCH();
+            // ---- [p_a p_b] = A [u_a u_b] in one pass --------------------------------------------------
+            const int nclL = cyc_count(L, g.py, g.y);
+            const int sw = (L > 12288) ? 4 : (L > 6144) ? 2 : 1;
+            Q.sw = sw;
+            const int nsc = (nclL + sw * TC - 1) / (sw * TC);
+            int gx = (nsc + 1) / 2, gy = 0;
+            if (nsc > 0) {
+                auto strip_rows_h = [&](int sc) {
+                    int tlast = std::min((sc + 1) * sw, (nclL + TC - 1) / TC) - 1;
+                    int clast = std::min((tlast + 1) * TC, nclL) - 1;
+                    if (clast < tlast * TC) return 0;
+                    long long cmax_g = (long long)clast * g.py + g.y;
+                    if (cmax_g <= g.x) return 0;
+                    return (int)((cmax_g - g.x - 1) / ((long long)TR * g.px)) + 1;
+                };
+                for (int bx = 0; bx < gx; bx++) {
+                    int s1 = nsc - 1 - bx, s2 = bx;
+                    int r = strip_rows_h(s1) + (s2 != s1 ? strip_rows_h(s2) : 0);
+                    if (r > gy) gy = r;
+                }
+            }
+            const int ntile_blocks = gx * gy;
+            const int nblocks = ntile_blocks + (Q.ndone > 0 ? NCH : 0);
+            mark(1);
+            if (nblocks > 0) {
+                symv2_kernel<<<nblocks, 256, 0, st>>>(Q, gx > 0 ? gx : 1, ntile_blocks);
+                EE_CHECK_LAUNCH();
+            }
+            mark(1);
+            // ---- p, alpha ----------------------------------------------------------------------------
+            const int nvb = (L + VR - 1) / VR;
+            if (!multi) {
+                pvec2_kernel<0><<<nvb, VR * VS, 0, st>>>(Q, pv, 0ull);
+                EE_CHECK_LAUNCH();
+            } else if (use_peer) {
+                const unsigned long long epoch = comm_peer_next_epoch();
+                pvec2_kernel<3><<<nvb, VR * VS, 0, st>>>(Q, pv, epoch);
+                EE_CHECK_LAUNCH();
+                pvec2_kernel<4><<<nvb, VR * VS, 0, st>>>(Q, pv, epoch);
+                EE_CHECK_LAUNCH();
+            } else {
+                pvec2_kernel<1><<<nvb, VR * VS, 0, st>>>(Q, pv, 0ull);
+                EE_CHECK_LAUNCH();
+                comm_allreduce_sum(P.pa, (size_t)npad + L, COMM_WORLD, st);
+                pvec2_kernel<2><<<nvb, VR * VS, 0, st>>>(Q, pv, 0ull);
+                EE_CHECK_LAUNCH();
+            }
+        }
+        if (stop) { col_end = 0; break; }
+        // ---- panel end: last pair -> panel, reflectors back into A, trailing rank-2k update ------
+        {
+            PrdP Q = P;
+            Q.k = -1; Q.first = 0; Q.has_next = 0;
+            next2_kernel<<<(i_base + 1 + VR - 1) / VR, VR * VS, 0, st>>>(Q);
+            EE_CHECK_LAUNCH();
+            dim3 grid((lda + 255) / 256, m0);
+            panel_restore_kernel<<<grid, 256, 0, st>>>(Q, 0);
+            EE_CHECK_LAUNCH();
+        }
+        const int nrl_b = cyc_count(i_base, g.px, g.x), ncl_b = cyc_count(i_base, g.py, g.y);
+        if (nrl_b > 0 && ncl_b > 0) {
+            PrdP Q = P;
+            int mx = nrl_b > ncl_b ? nrl_b : ncl_b;
+            dim3 grid((mx + 255) / 256, 2 * m0);
+            pack_uv_kernel<<<grid, 256, 0, st>>>(Q, UVx, lda, nrl_b, VUy, nclp, ncl_b, m0);
+            EE_CHECK_LAUNCH();
+            TriSpec tri; tri.mode = 1; tri.px = g.px; tri.py = g.py; tri.x = g.x; tri.y = g.y;
+            mark(2);
+            dgemm(st, 'N', 'T', nrl_b, ncl_b, 2 * m0, -1.0, UVx, lda, VUy, nclp, 1.0, A, lda, tri);
+            mark(2);
+        }
+    }
+    // ---- leading nrem x nrem block (prd_t8.F:207-315) ------------------------------------------------
+    {
+        PrdP Q = P;
+        prd_final_kernel<<<1, 32, 0, st>>>(Q, nrem);
+        EE_CHECK_LAUNCH();
+        if (multi) comm_allreduce_sum(P.scal + 16, 6, COMM_WORLD, st);
+        prd_final_store_kernel<<<1, 32, 0, st>>>(Q, nrem);
+        EE_CHECK_LAUNCH();
+    }
+    if (nrl > 0 && ncl > 0)
+        EE_CUDA(cudaMemcpy2DAsync(a_user, (size_t)lda_user * sizeof(double), A, (size_t)lda * sizeof(double),
+                                  (size_t)nrl * sizeof(double), ncl, cudaMemcpyDeviceToDevice, st));
+    EE_CUDA(cudaStreamSynchronize(st));
+    if (use_peer) {
+        int herr = 0;
+        EE_CUDA(cudaMemcpy(&herr, pv.err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (herr) fatal("peer all-reduce timed out waiting for another rank", __FILE__, __LINE__);
+    }
+    if (c.profiling >= 1) {
+        float t_symv = 0.f, t_syr2k = 0.f;
+        auto drain = [&](std::vector<cudaEvent_t> &pool, float &acc, bool trace) {
+            for (size_t i = 0; i + 1 < pool.size(); i += 2) {
+                float ms = 0.f; EE_CUDA(cudaEventElapsedTime(&ms, pool[i], pool[i + 1])); acc += ms;
+                if (trace) c.symv_trace.push_back(ms);
+            }
+            pool.clear();
+        };
+        drain(pool_symv, t_symv, true); drain(pool_syr2k, t_syr2k, false);
+        c.timings[5] = t_symv * 1e-3; c.timings[6] = t_syr2k * 1e-3;
+    }
+    dev_free(ws);
+    dev_free(A);
 }
 
 }  // namespace ee

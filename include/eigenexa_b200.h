@@ -103,11 +103,27 @@ int eigenexa_b200_dc(int n, int nvec, const double *d, const double *e, double *
 /* eigenvalues only by Sturm bisection (eigen_bisect, src/bisect.F:67)                 */
 int eigenexa_b200_bisect(int n, const double *d, const double *e, double *w);
 
+/* ---- penta-diagonal path of eigen_sx ------------------------------------------------
+ * eigen_prd(n,a,lda,d,e,ne,m)   src/eigen_prd.F:80    e is (ne x 2): e(:,1) = T(i-1,i),
+ *                                                      e(:,2) = T(i-2,i); reflectors of length i-2 in a
+ * eigen_dcx(n,nvec,d,e,ne,z,ldz,info,ret) src/dcx.F:75 band divide & conquer
+ * eigen_bisect2(d,e,f,w,n,mode)  src/bisect2.F:71
+ * eigen_common_trbakwy(...,nb)   src/trbakwy4.F:77     nb = 2 for the reflectors of eigen_prd */
+int eigenexa_b200_prd(int n, double *a, int lda, double *d, double *e, int ne, int m_forward);
+int eigenexa_b200_dcx(int n, int nvec, const double *d, const double *e, int ne, double *w,
+                      double *z, int ldz);
+int eigenexa_b200_bisect2(int n, const double *d, const double *e, int ne, double *w);
+int eigenexa_b200_trbakwy_nb(int n, int nvec, const double *a, int lda, double *z, int ldz,
+                             const double *e, int m_backward, int nb);
+
 /* ---- device-resident variant: a_dev / z_dev / w_dev are DEVICE pointers on this
  * rank's GPU (same layout).  Used to time the path with inputs already in HBM.       */
 int eigenexa_b200_eigen_s_dev(int n, int nvec, double *a_dev, int lda, double *w_dev,
                               double *z_dev, int ldz, int m_forward, int m_backward,
                               const char *mode);
+int eigenexa_b200_eigen_sx_dev(int n, int nvec, double *a_dev, int lda, double *w_dev,
+                               double *z_dev, int ldz, int m_forward, int m_backward,
+                               const char *mode);
 
 /* ---- benchmark/mat_set.f generators, written straight into device or host memory:
  * mtype 0 Frank, 1 Toeplitz, 2 random R+R^T (counter-based, seed), 3 Frank-2.        */

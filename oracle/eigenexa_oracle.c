@@ -326,6 +326,172 @@ void ora_trd(int n, double *a, int lda, double *d, double *e, int m_in)
 }
 
 /* ------------------------------------------------------------------ */
+/* eigen_prd: blocked reduction to penta-diagonal form, two columns per */
+/* step (src/eigen_prd.F:341-580).  Outputs d(1:n), e1(i) = T(i-1,i),   */
+/* e2(i) = T(i-2,i); reflector of column i (length i-2) left in a.      */
+/*   compute_u  src/eigen_prd_t4x.F:114-353 (two passes of Cholesky-QR  */
+/*              on the column pair, then two Householder reflectors)    */
+/*   au         src/eigen_prd_t2.F:153-206 (two right-hand sides)       */
+/*   compute_v  src/eigen_prd_t6_3.F:160-458 (panel corrections, 2x2    */
+/*              coupling c, V = (AU)C - U M with M + M^T = C^T U^T A U C)*/
+/*   local_2update src/eigen_prd_t5.F:69 ; panel load/store _t7.F:74,195 */
+/*   init/final src/eigen_prd_t8.F:75,207                               */
+/* ------------------------------------------------------------------ */
+void ora_prd(int n, double *a, int lda, double *d, double *e1, double *e2, int m_in)
+{
+    if (n <= 0) return;
+    for (int i = 0; i < n; i++) { d[i] = 0.0; e1[i] = 0.0; e2[i] = 0.0; }
+    const int nrem = 2 + n % 2;                 /* MBAND + mod(n, MBAND) leading columns stay */
+    size_t nn = (size_t)n;
+    if (n > nrem) {
+        int m = m_in < n ? m_in : n; m -= m % 2; if (m < 2) m = 2;
+        int mm = ((n - nrem) - 1) / m + 1 + 1;
+        double *W = (double *)calloc(nn * m, sizeof(double));
+        double *U = (double *)calloc(nn * m, sizeof(double));
+        double *V = (double *)calloc(nn * m, sizeof(double));
+        double *P = (double *)calloc(nn * 2, sizeof(double));
+        for (int i_block = mm; i_block >= 2; i_block--) {
+            int i_base = (i_block - 2) * m + nrem;
+            int m0 = m < n - i_base ? m : n - i_base;
+            if (m0 < 1) continue;
+            for (int k = 1; k <= m0; k++) {
+                double *wk = W + (size_t)(k - 1) * nn;
+                for (int j = 1; j <= n; j++) wk[j - 1] = (j <= i_base + k) ? A_(j, i_base + k) : 0.0;
+            }
+            memset(U, 0, nn * m * sizeof(double)); memset(V, 0, nn * m * sizeof(double));
+            for (int k1 = m0; k1 >= 2; k1 -= 2) {
+                const int i = i_base + k1, L = i - 2;
+                double *x2 = W + (size_t)(k1 - 1) * nn;   /* column i   -> u_x(:,2) */
+                double *x1 = W + (size_t)(k1 - 2) * nn;   /* column i-1 -> u_x(:,1) */
+                /* ---- compute_u ------------------------------------------------------ */
+                const double e1_i = x2[L];                /* A(i-1,i), u_t(8) */
+                double ut4 = 0, ut5 = 0, ut6 = 0, ut7 = 0, r12 = 0, s11 = 0, s12 = 0, s22 = 0;
+                int mask1 = 1, mask2 = 1;
+                for (int itr = 1; itr <= 2; itr++) {
+                    double u1 = 0.0, u2 = 0.0;
+                    for (int j = 0; j < L; j++) { u2 = fmax(u2, fabs(x2[j])); u1 = fmax(u1, fabs(x1[j])); }
+                    if (u1 == 0.0) u1 = 1.0;
+                    if (u2 == 0.0) u2 = 1.0;
+                    double t11 = 0, t12 = 0, t22 = 0;
+                    for (int j = 0; j < L; j++) {
+                        double t = x2[j] / u2, sj = x1[j] / u1;
+                        t11 += t * t; t12 += sj * t; t22 += sj * sj;
+                    }
+                    t12 *= u2 * u1; t11 *= u2 * u2; t22 *= u1 * u1;
+                    ut4 = (L >= 2) ? x1[L - 2] : 0.0; ut5 = x1[L - 1];
+                    if (itr == 1) { ut6 = (L >= 2) ? x2[L - 2] : 0.0; ut7 = x2[L - 1]; }
+                    if (t11 == 0.0) { mask2 = 0; s11 = 0.0; s12 = 0.0; s22 = t22; }
+                    else { mask2 = 1; s11 = t11; s12 = t12 / t11; s22 = t22 - s12 * t12; }
+                    mask1 = (s22 != 0.0);
+                    if (mask2) {
+                        if (mask1) {
+                            for (int j = 0; j < L; j++) x1[j] -= s12 * x2[j];
+                            ut4 -= s12 * ut6; ut5 -= s12 * ut7;
+                        }
+                    } else { for (int j = 0; j < L; j++) x2[j] = 0.0; ut6 = 0.0; ut7 = 0.0; }
+                    if (!mask1) { for (int j = 0; j < L; j++) x1[j] = 0.0; ut4 = 0.0; ut5 = 0.0; }
+                    r12 += s12;
+                }
+                const double rr1 = sqrt(s22 > 0.0 ? s22 : 0.0), rr2 = sqrt(s11);
+                double bet1 = 1.0, bet2 = 1.0, sgm1 = 0.0, sgm2 = 0.0;
+                if (mask2) {
+                    sgm2 = -sign_(rr2, ut7);
+                    x2[L - 1] -= sgm2; ut7 -= sgm2; bet2 = -ut7 * sgm2;
+                    if (mask1) {
+                        double sc = sgm2 * ut5 / bet2;
+                        for (int j = 0; j < L - 1; j++) x1[j] += sc * x2[j];
+                        ut4 += sc * ut6;
+                    }
+                }
+                if (mask1) {
+                    sgm1 = -sign_(rr1, ut4);
+                    if (L >= 2) x1[L - 2] -= sgm1;
+                    ut4 -= sgm1; bet1 = -ut4 * sgm1;
+                }
+                if (mask2) { x1[L - 1] = 0.0; x2[L] = 0.0; }
+                e1[i - 2] = sgm2 * r12; e1[i - 1] = e1_i; e2[i - 2] = sgm1; e2[i - 1] = sgm2;
+                const double c11 = 1.0 / bet1, c22 = 1.0 / bet2;
+                /* ---- au: P = A(1:L,1:L) [x1 x2] on the panel-start matrix ------------ */
+                double *p1 = P, *p2 = P + nn;
+#pragma omp parallel for schedule(static)
+                for (int r = 1; r <= L; r++) {
+                    double s1 = 0.0, s2 = 0.0;
+                    for (int c = 1; c <= L; c++) {
+                        double arc = (r <= c) ? A_(r, c) : A_(c, r);
+                        s1 += arc * x1[c - 1]; s2 += arc * x2[c - 1];
+                    }
+                    p1[r - 1] = s1; p2[r - 1] = s2;
+                }
+                /* ---- compute_v: corrections with the finished pairs of this panel ---- */
+                for (int l = k1 + 1; l <= m0; l++) {
+                    const double *ul = U + (size_t)(l - 1) * nn, *vl = V + (size_t)(l - 1) * nn;
+                    double vu1 = 0, uu1 = 0, vu2 = 0, uu2 = 0;
+                    for (int j = 0; j < L; j++) {
+                        vu1 += vl[j] * x1[j]; uu1 += ul[j] * x1[j];
+                        vu2 += vl[j] * x2[j]; uu2 += ul[j] * x2[j];
+                    }
+                    for (int j = 0; j < L; j++) {
+                        p1[j] -= ul[j] * vu1 + vl[j] * uu1;
+                        p2[j] -= ul[j] * vu2 + vl[j] * uu2;
+                    }
+                }
+                double g11 = 0, g12a = 0, g12b = 0, g22 = 0, g21 = 0;
+                for (int j = 0; j < L; j++) {
+                    g11 += x1[j] * p1[j]; g12a += x1[j] * p2[j]; g12b += x2[j] * p1[j]; g22 += x2[j] * p2[j];
+                    g21 += x2[j] * x1[j];
+                }
+                const double g12 = 0.5 * (g12a + g12b);
+                const double c12 = -c22 * c11 * g21;
+                double t11 = g11 * c11 + g12 * c12, t21 = g12 * c11 + g22 * c12, t12 = g12 * c22, t22 = g22 * c22;
+                double q11 = c11 * t11 + c12 * t21, q21 = c22 * t21, q12 = c11 * t12 + c12 * t22, q22 = c22 * t22;
+                const double m11 = 0.5 * q11, m12 = 0.5 * (q21 + q12), m22 = 0.5 * q22;
+                double *uk1 = U + (size_t)(k1 - 2) * nn, *uk2 = U + (size_t)(k1 - 1) * nn;
+                double *vk1 = V + (size_t)(k1 - 2) * nn, *vk2 = V + (size_t)(k1 - 1) * nn;
+                for (int j = 0; j < L; j++) {
+                    double y1 = p1[j] * c11 + p2[j] * c12, y2 = p2[j] * c22;
+                    uk1[j] = x1[j]; uk2[j] = x2[j];
+                    vk1[j] = y1 - x1[j] * m11 - x2[j] * m12;
+                    vk2[j] = y2 - x2[j] * m22;
+                }
+                /* ---- local_2update: the other panel columns at once ------------------ */
+                for (int c = 1; c <= k1 - 2; c++) {
+                    int gc = i_base + c;
+                    double *wc = W + (size_t)(c - 1) * nn;
+                    for (int q = 0; q < 2; q++) {
+                        const double *uq = q ? uk2 : uk1, *vq = q ? vk2 : vk1;
+                        double uc = uq[gc - 1], vc = vq[gc - 1];
+                        for (int j = 0; j < gc; j++) wc[j] -= uq[j] * vc + vq[j] * uc;
+                    }
+                }
+            }
+            /* panel store */
+            for (int k = 1; k <= m0; k++) {
+                int gc = i_base + k;
+                const double *wk = W + (size_t)(k - 1) * nn;
+                for (int j = 1; j <= gc; j++) A_(j, gc) = wk[j - 1];
+            }
+            /* rank-2k update of the trailing matrix (eigen_t1.F:250-306) */
+#pragma omp parallel for schedule(dynamic, 16)
+            for (int c = 1; c <= i_base; c++)
+                for (int k = 1; k <= m0; k++) {
+                    const double *uk = U + (size_t)(k - 1) * nn, *vk = V + (size_t)(k - 1) * nn;
+                    double uc = uk[c - 1], vc = vk[c - 1];
+                    double *col = &A_(1, c);
+                    for (int j = 1; j <= c; j++) col[j - 1] -= uk[j - 1] * vc + vk[j - 1] * uc;
+                }
+        }
+        free(W); free(U); free(V); free(P);
+    }
+    /* eigen_prd_final (prd_t8.F:207-315) */
+    for (int i = (nrem < n ? nrem : n); i >= 2; i--) {
+        e1[i - 1] = A_(i - 1, i); A_(i - 1, i) = 0.0;
+        if (i - 2 >= 1) { e2[i - 1] = A_(i - 2, i); A_(i - 2, i) = 0.0; }
+    }
+    for (int j = 1; j <= n; j++) d[j - 1] = A_(j, j);
+    e1[0] = 0.0; e2[0] = 0.0; if (n >= 2) e2[1] = 0.0;
+}
+
+/* ------------------------------------------------------------------ */
 /* eigen_common_trbakwy: Z <- H_n ... H_2 Z                            */
 /* a: output of ora_trd; e: off-diagonal from ora_trd (clobbered like  */
 /* the reference's beta); z: n x nvec, ldz; m_b block; iblk = 1        */

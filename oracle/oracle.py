@@ -49,6 +49,7 @@ def lib() -> C.CDLL:
         L.ora_scaling.argtypes = [C.c_int, dp, C.c_int]
         L.ora_scaling.restype = C.c_double
         L.ora_trd.argtypes = [C.c_int, dp, C.c_int, dp, dp, C.c_int]
+        L.ora_prd.argtypes = [C.c_int, dp, C.c_int, dp, dp, dp, C.c_int]
         L.ora_trbakwy.argtypes = [C.c_int, C.c_int, dp, C.c_int, dp, C.c_int, dp, C.c_int, C.c_int]
         L.ora_bisect.argtypes = [C.c_int, dp, dp, dp]
         L.ora_mat_set_local.argtypes = [C.c_int, C.c_int, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -115,13 +116,48 @@ def trd(a: np.ndarray, m_f: int = 48):
     return d, e
 
 
-def trbakwy(a: np.ndarray, e: np.ndarray, z: np.ndarray, m_b: int = 128, nvec: int | None = None):
-    """Back-transform the first nvec columns of Fortran-ordered z in place."""
+def prd(a: np.ndarray, m_f: int = 48):
+    """Reduce (upper triangle of) Fortran-ordered ``a`` to penta-diagonal form in place
+    (eigen_prd, src/eigen_prd.F:341-580).  Returns (d, e1, e2): e1[i] = T(i-1,i), e2[i] = T(i-2,i)."""
+    assert a.flags.f_contiguous
+    n = a.shape[1]
+    d, e1, e2 = np.zeros(n), np.zeros(n), np.zeros(n)
+    lib().ora_prd(n, _dp(a), a.shape[0], _dp(d), _dp(e1), _dp(e2), m_f)
+    return d, e1, e2
+
+
+def band_from(d: np.ndarray, e1: np.ndarray, e2: np.ndarray) -> np.ndarray:
+    """Dense symmetric penta-diagonal matrix of (d, e1, e2)."""
+    n = d.shape[0]
+    b = np.diag(d)
+    if n > 1:
+        b += np.diag(e1[1:], 1) + np.diag(e1[1:], -1)
+    if n > 2:
+        b += np.diag(e2[2:], 2) + np.diag(e2[2:], -2)
+    return b
+
+
+def band_eig(d: np.ndarray, e1: np.ndarray, e2: np.ndarray):
+    """Eigen-decomposition of the penta-diagonal matrix (stands in for eigen_dcx, src/dcx.F:75): LAPACK
+    dsbevd from SciPy's OpenBLAS on the upper band storage."""
+    from scipy.linalg import eig_banded
+    n = d.shape[0]
+    ab = np.zeros((3, n))
+    ab[2] = d
+    ab[1, 1:] = e1[1:]
+    ab[0, 2:] = e2[2:]
+    w, z = eig_banded(ab, lower=False)
+    return w, np.asfortranarray(z)
+
+
+def trbakwy(a: np.ndarray, e: np.ndarray, z: np.ndarray, m_b: int = 128, nvec: int | None = None, iblk: int = 1):
+    """Back-transform the first nvec columns of Fortran-ordered z in place (iblk = 1: reflectors of
+    eigen_trd, length i-1; iblk = 2: reflectors of eigen_prd, length i-2, with e = e2)."""
     assert a.flags.f_contiguous and z.flags.f_contiguous
     n = a.shape[1]
     nvec = z.shape[1] if nvec is None else nvec
     beta = np.array(e, dtype=np.float64, copy=True)
-    lib().ora_trbakwy(n, nvec, _dp(a), a.shape[0], _dp(z), z.shape[0], _dp(beta), m_b, 1)
+    lib().ora_trbakwy(n, nvec, _dp(a), a.shape[0], _dp(z), z.shape[0], _dp(beta), m_b, iblk)
     return z
 
 
@@ -165,6 +201,29 @@ def eigen_s(a: np.ndarray, nvec: int | None = None, m_f: int = 48, m_b: int = 12
     w, z = tridiag_eig(d, e)
     z = np.asfortranarray(z[:, :abs(nvec)])
     trbakwy(a, e, z, m_b)
+    if sigma != 1.0 and sigma != 0.0:
+        w = w * (1.0 / sigma)
+    return w, z
+
+
+def eigen_sx(a: np.ndarray, nvec: int | None = None, m_f: int = 48, m_b: int = 128, mode: str = "A"):
+    """Restatement of eigen_sx (src/eigen_sx.F:30-308) on a 1x1 grid: scaling, eigen_prd, band
+    eigensolver, back-transformation with MBAND = 2."""
+    assert a.flags.f_contiguous
+    n = a.shape[1]
+    nvec = n if nvec is None else nvec
+    if nvec == 0:
+        mode = "N"
+    m_b = max(1, min(m_b, n))
+    sigma = scaling(a)
+    if np.isnan(sigma):
+        return np.full(n, np.nan), None
+    d, e1, e2 = prd(a, m_f)
+    w, z = band_eig(d, e1, e2)
+    if mode == "N":
+        return w, None
+    z = np.asfortranarray(z[:, :abs(nvec)])
+    trbakwy(a, e2, z, m_b, iblk=2)
     if sigma != 1.0 and sigma != 0.0:
         w = w * (1.0 / sigma)
     return w, z

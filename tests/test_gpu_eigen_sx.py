@@ -1,0 +1,117 @@
+"""GPU parity of the penta-diagonal path (eigen_sx): eigen_prd, eigen_dcx, eigen_bisect2, the
+back-transformation with nb = 2 and the full driver, through the C ABI vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+F = lambda x: np.array(x, order="F", copy=True)
+
+
+@pytest.mark.parametrize("n,mtype,mf", [(4, 2, 48), (5, 2, 2), (6, 0, 48), (7, 2, 4), (64, 0, 48), (100, 2, 6),
+                                        (129, 2, 48), (300, 0, 48), (513, 2, 48), (1000, 0, 48), (1500, 2, 48),
+                                        (777, 3, 32), (600, 1, 48)])
+def test_prd_matches_oracle(ee, n, mtype, mf):
+    a = O.mat_set(n, mtype)
+    ao = F(a)
+    do, e1o, e2o = O.prd(ao, mf)
+    ag = F(a)
+    dg, e1g, e2g = ee.eigen_prd(n, ag, mf)
+    full = O.sym_from_upper(a)
+    nrm = np.linalg.norm(full)
+    tol = 10 * n * O.EPS * nrm   # same bound BASELINE.json states for (d, e) of eigen_trd
+    assert np.abs(dg - do).max() <= tol
+    assert np.abs(e1g - e1o).max() <= tol
+    assert np.abs(e2g - e2o).max() <= tol
+    # the band matrix is orthogonally similar to A
+    wb = np.linalg.eigvalsh(O.band_from(dg, e1g, e2g))
+    assert np.abs(wb - np.linalg.eigvalsh(full)).max() <= tol
+
+
+@pytest.mark.parametrize("n,kind", [(3, "rand"), (5, "rand"), (33, "rand"), (64, "rand"), (100, "rand"), (257, "rand"),
+                                    (1000, "rand"), (500, "const"), (400, "graded"), (300, "zeroe"), (600, "prd")])
+def test_dcx_penta(ee, n, kind):
+    rng = np.random.default_rng(n)
+    if kind == "rand":
+        d, e1, e2 = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(n)
+    elif kind == "const":
+        d, e1, e2 = np.full(n, 6.0), np.full(n, -4.0), np.full(n, 1.0)     # biharmonic stencil: heavy deflation
+    elif kind == "graded":
+        g = 10.0 ** (-np.arange(n) / 40.0)
+        d, e1, e2 = g.copy(), 0.1 * g, 0.01 * g
+    elif kind == "zeroe":
+        d, e1, e2 = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(n)
+        e1[::7] = 0.0; e2[::5] = 0.0
+    else:
+        d, e1, e2 = O.prd(O.mat_set(n, 2), 48)
+    e1[0] = 0.0; e2[:2] = 0.0
+    z = np.zeros((n, n), order="F")
+    w = ee.eigen_dcx(n, d, e1, e2, z)
+    B = O.band_from(d, e1, e2)
+    wl = np.linalg.eigvalsh(B)
+    nrm = max(np.linalg.norm(B), 1e-300)
+    assert np.all(np.diff(w) >= 0)
+    assert np.abs(w - wl).max() <= 10 * n * O.EPS * nrm
+    res, orth = O.ev_test(B, w, z)
+    assert res <= 10 and orth <= 10, (res, orth)
+
+
+@pytest.mark.parametrize("n", [3, 50, 1000])
+def test_bisect2(ee, n):
+    rng = np.random.default_rng(n)
+    d, e1, e2 = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(n)
+    e1[0] = 0.0; e2[:2] = 0.0
+    w = ee.eigen_bisect2(n, d, e1, e2)
+    B = O.band_from(d, e1, e2)
+    assert np.abs(w - np.linalg.eigvalsh(B)).max() <= 10 * n * O.EPS * max(np.linalg.norm(B), 1.0)
+
+
+@pytest.mark.parametrize("n,mtype,mb,nvec", [(5, 2, 128, 5), (50, 2, 8, 50), (300, 0, 128, 300), (513, 2, 128, 513),
+                                             (1000, 2, 128, 250)])
+def test_trbak_nb2_matches_oracle(ee, n, mtype, mb, nvec):
+    a = O.mat_set(n, mtype)
+    ao = F(a)
+    d, e1, e2 = O.prd(ao, 48)
+    w, zt = O.band_eig(d, e1, e2)
+    zt = F(zt[:, :nvec])
+    zo = O.trbakwy(ao, e2, F(zt), mb, iblk=2)
+    zg = ee.eigen_trbakwy(n, ao, F(zt), e2, mb, nvec=nvec, nb=2)
+    assert np.abs(zg - zo).max() <= 50 * n * O.EPS
+    res, orth = O.ev_test(O.sym_from_upper(a), w[:nvec], zg)
+    assert res <= 10 and orth <= 10
+
+
+@pytest.mark.parametrize("n,mtype,mf,mb", [(1, 0, 48, 128), (2, 2, 48, 128), (3, 2, 48, 128), (4, 2, 48, 128),
+                                           (10, 2, 4, 4), (100, 0, 48, 128), (257, 2, 48, 128), (1000, 0, 48, 128),
+                                           (1501, 2, 48, 128), (2000, 2, 48, 128), (900, 3, 32, 64)])
+def test_eigen_sx_all_pairs(ee, n, mtype, mf, mb):
+    a = O.mat_set(n, mtype)
+    full = O.sym_from_upper(a)
+    w, z = np.zeros(n), np.zeros((n, n), order="F")
+    ee.eigen_sx(n, F(a), w, z, m_forward=mf, m_backward=mb, mode="A")
+    wl = np.linalg.eigvalsh(full)
+    tol = 10 * n * O.EPS * np.linalg.norm(full)
+    assert np.abs(w - wl).max() <= tol
+    wo, _ = O.eigen_sx(F(a), m_f=mf, m_b=mb)
+    assert np.abs(w - wo).max() <= tol
+    res, orth = O.ev_test(full, w, z)
+    assert res <= 10 and orth <= 10, (res, orth)
+
+
+def test_eigen_sx_mode_n_and_partial(ee):
+    n = 700
+    a = O.mat_set(n, 2)
+    full = O.sym_from_upper(a)
+    wl = np.linalg.eigvalsh(full)
+    tol = 10 * n * O.EPS * np.linalg.norm(full)
+    w, z = np.zeros(n), np.zeros((n, n), order="F")
+    ee.eigen_sx(n, F(a), w, z, nvec=0, mode="N")
+    assert np.abs(w - wl).max() <= tol
+    nvec = 100
+    w, z = np.zeros(n), np.zeros((n, nvec), order="F")
+    ee.eigen_sx(n, F(a), w, z, nvec=nvec, mode="A")
+    assert np.abs(w - wl).max() <= tol
+    res, orth = O.ev_test(full, w[:nvec], z)
+    assert res <= 10 and orth <= 10

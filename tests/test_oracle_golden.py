@@ -136,3 +136,23 @@ def test_cyclic_scatter_gather_roundtrip():
                 assert np.array_equal(loc, gen)
                 parts[(x, y)] = loc
         assert np.array_equal(O.gather_cyclic(parts, n, n, px, py), a)
+
+
+@pytest.mark.parametrize("n,mt,mf", [(3, 2, 48), (4, 0, 48), (5, 2, 2), (10, 2, 4), (33, 0, 48), (200, 2, 48), (301, 3, 32)])
+def test_prd_restatement_is_an_orthogonal_band_reduction(n, mt, mf):
+    """eigen_prd restated (src/eigen_prd.F:341-580): the penta-diagonal (d, e1, e2) has the spectrum of A, the
+    reflectors left in a rebuild A's eigenvectors (nb = 2 back-transformation), Frank matrices hit the
+    closed-form spectrum of benchmark/mat_set.f:638-647."""
+    a = O.mat_set(n, mt)
+    full = O.sym_from_upper(a)
+    a2 = np.array(a, order="F")
+    d, e1, e2 = O.prd(a2, mf)
+    assert e1[0] == 0 and e2[0] == 0 and (n < 2 or e2[1] == 0)
+    tol = 10 * n * O.EPS * np.linalg.norm(full)
+    wb = np.linalg.eigvalsh(O.band_from(d, e1, e2))
+    assert np.abs(wb - np.linalg.eigvalsh(full)).max() <= tol
+    w, z = O.eigen_sx(np.array(a, order="F"), m_f=mf)
+    res, orth = O.ev_test(full, w, z)
+    assert res <= 10 and orth <= 10
+    if mt == 0:
+        assert np.abs(w - O.w_set(n, 0)).max() <= tol

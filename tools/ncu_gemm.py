@@ -1,4 +1,5 @@
-"""Short ncu target for the DMMA GEMM: three launches on the shapes of the path."""
+"""Short ncu target for the DMMA GEMM: two launches per shape on the shapes of the path.
+   python tools/ncu_gemm.py [small|all]"""
 import sys, torch
 sys.path.insert(0, ".")
 import eigenexa_b200 as E
@@ -12,8 +13,10 @@ def run(ta, tb, m, n, k, beta):
     for _ in range(2):
         E.dgemm_dev(ta, tb, m, n, k, -1.0, A.data_ptr(), ar, B.data_ptr(), br, beta, Cm.data_ptr(), m)
     E.sync()
-run("N", "N", 8192, 8192, 8192, 0.0)      # merge GEMM (128x128 tiles)
-run("N", "T", 16384, 16384, 256, 1.0)     # trailing update, K = 2*128 (128x64 tiles)
-run("T", "N", 256, 16384, 16384, 0.0)     # V^T Z
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+run("N", "T", 16384, 16384, 256, 1.0)         # trailing update, K = 2*128
+if which == "all":
+    run("N", "N", 8192, 8192, 8192, 0.0)      # merge GEMM
+    run("T", "N", 256, 16384, 16384, 0.0)     # V^T Z
 E.eigen_free()
 print("ok")
