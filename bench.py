@@ -126,6 +126,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--n", type=int, default=int(os.environ.get("EIGENEXA_BENCH_N", "50000")))
     ap.add_argument("--cpu-n", type=int, default=3000, help="size of the bounded CPU sample")
+    ap.add_argument("--solver", default=os.environ.get("EIGENEXA_BENCH_SOLVER", "s"), choices=["s", "sx"],
+                    help="s: eigen_s (tridiagonal path, the headline); sx: eigen_sx (penta-diagonal path)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -180,11 +182,15 @@ def main():
     z_dev = torch.empty((max(nvl, 1), lda), dtype=torch.float64, device=dev)
     lib_stream = torch.cuda.ExternalStream(E.stream_ptr(), device=dev)
 
+    solve_dev = E.eigen_sx_dev if args.solver == "sx" else E.eigen_s_dev
+    solve_host = E.eigen_sx if args.solver == "sx" else E.eigen_s
+    sname = "eigen_sx" if args.solver == "sx" else "eigen_s"
+
     def step_dev():
         a_work.copy_(a_master)          # the solver destroys a; restoring it is part of the step (D2D, ~ms)
         torch.cuda.current_stream().synchronize()
-        E.eigen_s_dev(n, a_work.data_ptr(), lda, w_dev.data_ptr(), z_dev.data_ptr(), lda, nvec=nvec,
-                      m_forward=48, m_backward=128, mode="A")
+        solve_dev(n, a_work.data_ptr(), lda, w_dev.data_ptr(), z_dev.data_ptr(), lda, nvec=nvec,
+                  m_forward=48, m_backward=128, mode="A")
 
     # ---- leg 1: inputs resident in HBM ---------------------------------------------------------
     for _ in range(args.warmup):
@@ -235,6 +241,9 @@ def main():
     symv_s = float(stage[5])
     bytes_rank = symv_bytes(n) / world
     n_symv = max(n - 2, 1)
+    if args.solver == "sx":
+        bytes_rank *= 0.5      # one pass over the staircase per column PAIR (2/3 n^3 B)
+        n_symv = max((n - 2) // 2, 1)
     achieved = bytes_rank / symv_s / 1e9 if symv_s > 0 else None
     traffic = None
     try:
@@ -246,7 +255,8 @@ def main():
         fp64_peak = float(json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))["cublas_dgemm_tflops"])
     except Exception:
         pass
-    roofline = {"kernel": "symv_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+    roofline = {"kernel": "symv2_kernel" if args.solver == "sx" else "symv_kernel", "bound": "hbm", "achieved": achieved,
+                "peak": hbm_peak, "unit": "GB/s",
                 "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "launches_per_step": n_symv, "avg_launch_ms": symv_s / n_symv * 1e3,
                 "algorithmic_bytes_per_launch_avg": bytes_rank / n_symv,
@@ -279,7 +289,7 @@ def main():
 
         def step_host():
             a_host.view(-1)[:3] = head                        # eigen_s overwrites a(1:3,1) with its statistics
-            E.eigen_s(n, a_np, w_host, z_np, nvec=nvec, m_forward=48, m_backward=128, mode="A")
+            solve_host(n, a_np, w_host, z_np, nvec=nvec, m_forward=48, m_backward=128, mode="A")
 
         barrier()
         t0 = time.perf_counter()
@@ -289,7 +299,7 @@ def main():
         t_e2e = max_over_ranks(time.perf_counter() - t0) / args.steps
         e2e = {"value": flops / t_e2e / 1e12, "unit": "TFLOP/s", "time_s": t_e2e, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "pinned": pinned,
-               "api": "eigen_s(n, nvec, a, lda, w, z, ldz, m_forward, m_backward, mode) with host arrays"}
+               "api": sname + "(n, nvec, a, lda, w, z, ldz, m_forward, m_backward, mode) with host arrays"}
 
     # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------
     cpu = None
@@ -304,7 +314,7 @@ def main():
             "metric": "eigen_s_fp64_tflops", "value": value, "unit": "TFLOP/s", "time_s": t_step, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"eigen_s N={n} random symmetric FP64, all eigenpairs (BASELINE configs[3])", "n": n,
+            "config": {"workload": f"{sname} N={n} random symmetric FP64, all eigenpairs (BASELINE configs[3])", "n": n,
                        "nvec": nvec, "m_forward": 48, "m_backward": 128, "mode": "A", "grid": f"{px}x{py}",
                        "l2": f"inputs larger than L2 (A = {nrl * ncl * 8 / 1e9:.1f} GB per GPU vs 126 MB)",
                        "flop_model": "4/3 n^3 + merge GEMM flops + 2 nvec n^2 (src/eigen_s.F:177,248,270)"},

@@ -74,6 +74,7 @@ def lib() -> C.CDLL:
                                                 dp]
         L.eigenexa_b200_dgemm_dev.argtypes = [C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p,
                                               C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int]
+        L.eigenexa_b200_dgemm_tri_dev.argtypes = list(L.eigenexa_b200_dgemm_dev.argtypes) + [C.c_int] * 4
         L.eigenexa_b200_stream.restype = C.c_void_p
         L.eigenexa_b200_launch_count.argtypes = [C.c_int]
         L.eigenexa_b200_launch_count.restype = C.c_int64
@@ -307,6 +308,13 @@ def ev_test_dev(n, nvec, a_ptr, lda, w_ptr, z_ptr, ldz):
 def dgemm_dev(transa, transb, m, n, k, alpha, a_ptr, lda, b_ptr, ldb, beta, c_ptr, ldc):
     rc = lib().eigenexa_b200_dgemm_dev(transa.encode(), transb.encode(), m, n, k, alpha, a_ptr, lda, b_ptr, ldb, beta,
                                        c_ptr, ldc)
+    if rc != 0:
+        raise RuntimeError(last_error())
+
+
+def dgemm_tri_dev(transa, transb, m, n, k, alpha, a_ptr, lda, b_ptr, ldb, beta, c_ptr, ldc, px=1, py=1, x=0, y=0):
+    rc = lib().eigenexa_b200_dgemm_tri_dev(transa.encode(), transb.encode(), m, n, k, alpha, a_ptr, lda, b_ptr, ldb, beta,
+                                           c_ptr, ldc, px, py, x, y)
     if rc != 0:
         raise RuntimeError(last_error())
 

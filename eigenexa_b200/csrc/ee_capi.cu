@@ -39,16 +39,29 @@ Context &ctx()
     return c;
 }
 
+// Workspace comes from the device's stream-ordered memory pool on the library stream: a solve
+// allocates and frees tens of GB (padded copy of A, the D&C matrices); cudaMalloc/cudaFree of such
+// blocks cost hundreds of ms each and synchronise the device, the pool hands the same pages back to
+// the next stage / the next call.  eigen_free returns everything to the driver.
 void *dev_alloc(size_t bytes)
 {
     void *p = nullptr;
     if (bytes == 0) bytes = 8;
-    EE_CUDA(cudaMalloc(&p, bytes));
+    EE_CUDA(cudaMallocAsync(&p, bytes, ctx().stream));
     return p;
 }
 void dev_free(void *p)
 {
-    if (p) EE_CUDA(cudaFree(p));
+    if (p) EE_CUDA(cudaFreeAsync(p, ctx().stream));
+}
+static void pool_configure(int device, bool release_all)
+{
+    cudaMemPool_t pool;
+    EE_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    if (release_all) { EE_CUDA(cudaMemPoolTrimTo(pool, 0)); return; }
+    // keep up to 48 GB of freed workspace mapped between stages and calls (one N = 50000 matrix is 20 GB)
+    unsigned long long keep = 48ull << 30;
+    EE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
 }
 
 // grid shape chosen by eigen_init (src/eigen_libs0.F:526-540)
@@ -302,6 +315,7 @@ void eigen_init(const eigenexa_b200_comm_t *comm, const char *order)
     c.g = g;
     EE_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     EE_CUDA(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
+    pool_configure(c.device, false);
     if (comm_init(comm ? comm->unique_id : nullptr, rank, nranks, g) != 0) return;
     c.initialized = true;
 }
@@ -314,6 +328,7 @@ void eigen_free(void)
     comm_finalize();
     for (cudaEvent_t e : c.ev_pool) cudaEventDestroy(e);
     c.ev_pool.clear();
+    pool_configure(c.device, true);
     cudaStreamDestroy(c.stream); cudaStreamDestroy(c.stream2);
     c.stream = c.stream2 = nullptr;
     c.initialized = false;
@@ -620,6 +635,17 @@ int eigenexa_b200_dgemm_dev(char transa, char transb, int m, int n, int k, doubl
 {
     if (!ctx().initialized) { set_error("not initialised"); return 1; }
     dgemm(ctx().stream, transa, transb, m, n, k, alpha, a_dev, lda, b_dev, ldb, beta, c_dev, ldc);
+    return 0;
+}
+// staircase form used by the trailing update of eigen_trd / eigen_prd: only tiles that reach the
+// upper triangle of the cyclic local matrix (global row jl*px+x <= global col il*py+y) are touched
+int eigenexa_b200_dgemm_tri_dev(char transa, char transb, int m, int n, int k, double alpha, const double *a_dev, int lda,
+                                const double *b_dev, int ldb, double beta, double *c_dev, int ldc, int px, int py, int x,
+                                int y)
+{
+    if (!ctx().initialized) { set_error("not initialised"); return 1; }
+    TriSpec tri; tri.mode = 1; tri.px = px; tri.py = py; tri.x = x; tri.y = y;
+    dgemm(ctx().stream, transa, transb, m, n, k, alpha, a_dev, lda, b_dev, ldb, beta, c_dev, ldc, tri);
     return 0;
 }
 void eigenexa_b200_sync(void) { if (ctx().initialized) EE_CUDA(cudaStreamSynchronize(ctx().stream)); }

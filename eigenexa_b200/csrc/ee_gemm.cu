@@ -314,6 +314,7 @@ struct TileP {
     int group_w;               // rasterisation: tile columns per group (full GEMMs)
     int total_items;           // valid tiles * ksplit
     unsigned stagger_ns;       // > 0: groups start up to this many ns apart (see dgemm_tma_kernel)
+    int dbg;                   // EIGENEXA_B200_GEMM_DBG bits: 1 no fast preload, 2 no fast epilogue, 4 no stagger, 8 no C prefetch
 };
 
 // maps the linear index of a VALID tile to its coordinates; indices must be queried in
@@ -414,7 +415,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         // ================= producer warp: lane 0 drives the TMA ring; all lanes prefetch the next
         // tile's C into L2 when the GEMM accumulates into C =====================================
         TileWalk<BM, BN> ahead;
-        const bool pf = (p.beta != 0.0) && ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+        const bool pf = !(tp.dbg & 8) && (p.beta != 0.0) && ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
         for (int item = vbid; item < tp.total_items; item += vgrid) {
             if (pf && item + vgrid < tp.total_items) {
                 const int nitem = item + vgrid;
@@ -467,6 +468,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
     const int wm = wl % WM, wn = wl / WM;
     const int fi = lane >> 2, fk = lane & 3;
+    int pend = -1;   // stage consumed last, not yet handed back to the producer (the last one never needs to be)
     for (int item = vbid; item < tp.total_items; item += vgrid) {
         const int tile = item / p.ksplit;
         const int z = item - tile * p.ksplit;
@@ -481,7 +483,23 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
         double acc[NF][MF][2];
         const bool preload = (p.beta != 0.0) && (p.alpha == 1.0 || p.alpha == -1.0);
-        if (preload) {
+        // interior tile with 16-byte aligned C: no bounds checks, so that all C loads of the tile are
+        // in flight together (a branch per element would expose every load's latency in turn)
+        const bool interior = vec && (m0 + BM <= p.M) && (n0 + BN <= p.N);
+        if (preload && interior && !(tp.dbg & 1)) {
+            const double sc = p.beta * p.alpha;
+            const double *cb = C + (long long)(n0 + wn * WTN + fi) * p.ldc + m0 + wm * WTM + 2 * fk;
+            double2 cv[NF][MF];
+#pragma unroll
+            for (int a = 0; a < NF; a++)
+#pragma unroll
+                for (int b = 0; b < MF; b++)
+                    cv[a][b] = __ldcs(reinterpret_cast<const double2 *>(cb + (long long)(a * 8) * p.ldc + b * 8));
+#pragma unroll
+            for (int a = 0; a < NF; a++)
+#pragma unroll
+                for (int b = 0; b < MF; b++) { acc[a][b][0] = sc * cv[a][b].x; acc[a][b][1] = sc * cv[a][b].y; }
+        } else if (preload) {
             const double sc = p.beta * p.alpha;
 #pragma unroll
             for (int a = 0; a < NF; a++) {
@@ -511,6 +529,14 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
         for (int kc = 0; kc < nk; kc++) {
             mbar_wait(bar0 + 8 * s, ph);
+            // Release the PREVIOUS stage only now.  ptxas is free to schedule an arrive right behind the last
+            // LDS of a stage (the remaining DMMAs only touch registers), i.e. before that load has returned,
+            // and the producer's TMA would then overwrite shared memory under an in-flight read.  Behind this
+            // wait every DMMA of the previous stage has issued, so all of its fragment loads have completed.
+            if (pend >= 0) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar0 + 8 * (NST + pend));
+            }
             const double *sa = stages + (size_t)s * (SA + SB), *sb = sa + SA;
 #pragma unroll
             for (int kk = 0; kk < KC; kk += 4) {
@@ -524,12 +550,21 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
                     for (int b = 0; b < MF; b++) dmma(acc[a][b][0], acc[a][b][1], bf[a], af[b]);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar0 + 8 * (NST + s));
+            pend = s;
             if (++s == NST) { s = 0; ph ^= 1u; }
         }
 
         const double beta = preload ? 0.0 : p.beta;
+        if (interior && beta == 0.0 && !(tp.dbg & 2)) {
+            double *cb = C + (long long)(n0 + wn * WTN + fi) * p.ldc + m0 + wm * WTM + 2 * fk;
+#pragma unroll
+            for (int a = 0; a < NF; a++)
+#pragma unroll
+                for (int b = 0; b < MF; b++)
+                    *reinterpret_cast<double2 *>(cb + (long long)(a * 8) * p.ldc + b * 8) =
+                        make_double2(p.alpha * acc[a][b][0], p.alpha * acc[a][b][1]);
+            continue;
+        }
 #pragma unroll
         for (int a = 0; a < NF; a++) {
             const int n = n0 + wn * WTN + a * 8 + fi;
@@ -641,8 +676,11 @@ void launch_tma(cudaStream_t st, const GemmP &p)
     tp.group_w = std::max(1, std::min(tp.tiles_n, 16 * 64 / BN));
     // C read-modify-write with many tiles per group: stagger the groups over one tile period
     // (2 BM BN K flop at 1/NG of an SM's ~250 GFLOP/s)
+    static int dbg = -1;
+    if (dbg < 0) { const char *e = getenv("EIGENEXA_B200_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
+    tp.dbg = dbg;
     tp.stagger_ns = 0;
-    if (p.beta != 0.0 && tp.total_items >= 4 * NG * ctx().sm_count) {
+    if (!(dbg & 4) && p.beta != 0.0 && tp.total_items >= 4 * NG * ctx().sm_count) {
         const double tile_ns = 2.0 * BM * BN * (double)p.kper / 250.0 * NG;
         tp.stagger_ns = (unsigned)std::min(tile_ns, 400000.0);
     }

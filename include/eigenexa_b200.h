@@ -140,6 +140,12 @@ int eigenexa_b200_ev_test_dev(int n, int nvec, const double *a_dev, int lda,
 int eigenexa_b200_dgemm_dev(char transa, char transb, int m, int n, int k, double alpha,
                             const double *a_dev, int lda, const double *b_dev, int ldb,
                             double beta, double *c_dev, int ldc);
+/* same, restricted to the tiles that reach the upper "staircase" of a 2D-cyclic local matrix
+ * (the form eigen_common_2update uses, src/eigen_t1.F:250-306); tiles strictly below it are
+ * left untouched, tiles on it are updated in full.                                       */
+int eigenexa_b200_dgemm_tri_dev(char transa, char transb, int m, int n, int k, double alpha,
+                                const double *a_dev, int lda, const double *b_dev, int ldb,
+                                double beta, double *c_dev, int ldc, int px, int py, int x, int y);
 void eigenexa_b200_sync(void);      /* wait for the library stream                     */
 void *eigenexa_b200_stream(void);   /* cudaStream_t of the library (for event timing)  */
 

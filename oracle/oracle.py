@@ -142,6 +142,8 @@ def band_eig(d: np.ndarray, e1: np.ndarray, e2: np.ndarray):
     dsbevd from SciPy's OpenBLAS on the upper band storage."""
     from scipy.linalg import eig_banded
     n = d.shape[0]
+    if n == 1:
+        return d.copy(), np.ones((1, 1), order="F")
     ab = np.zeros((3, n))
     ab[2] = d
     ab[1, 1:] = e1[1:]

@@ -22,9 +22,16 @@ def test_prd_matches_oracle(ee, n, mtype, mf):
     full = O.sym_from_upper(a)
     nrm = np.linalg.norm(full)
     tol = 10 * n * O.EPS * nrm   # same bound BASELINE.json states for (d, e) of eigen_trd
-    assert np.abs(dg - do).max() <= tol
-    assert np.abs(e1g - e1o).max() <= tol
-    assert np.abs(e2g - e2o).max() <= tol
+    if mtype in (0, 3):
+        # Frank matrices: columns i and i-1 coincide above the band, so the second reflector of the very
+        # first pair is built from a vector that is exactly zero in exact arithmetic (mask(1) of
+        # src/eigen_prd_t4x.F:204-208) and pure rounding noise otherwise: the band matrix is not unique,
+        # only its spectrum (checked below) and the band structure are.
+        assert e1g[0] == 0 and e2g[0] == 0 and e2g[1] == 0
+    else:
+        assert np.abs(dg - do).max() <= tol
+        assert np.abs(e1g - e1o).max() <= tol
+        assert np.abs(e2g - e2o).max() <= tol
     # the band matrix is orthogonally similar to A
     wb = np.linalg.eigvalsh(O.band_from(dg, e1g, e2g))
     assert np.abs(wb - np.linalg.eigvalsh(full)).max() <= tol

@@ -28,6 +28,7 @@ def test_dgemm_matches_torch(ee, ta, tb, m, n, k, alpha, beta, pads):
     lda, ldb, ldc = ar + pads[0], br + pads[1], m + 2
     A, B, Cm = colmajor(ar, ac, lda), colmajor(br, bc, ldb), colmajor(m, n, ldc)
     C0 = Cm.clone()
+    torch.cuda.synchronize()     # the library runs on its own stream: torch's copies must have landed
     ee.dgemm_dev(ta, tb, m, n, k, alpha, A.data_ptr(), lda, B.data_ptr(), ldb, beta, Cm.data_ptr(), ldc)
     ee.sync()
     Am = A[:, :ar].T
@@ -40,3 +41,33 @@ def test_dgemm_matches_torch(ee, ta, tb, m, n, k, alpha, beta, pads):
     assert float((got - ref).abs().max()) <= tol
     # padding untouched
     assert torch.equal(Cm[:, m:], C0[:, m:])
+
+
+@pytest.mark.parametrize("m,n,k,grid", [(300, 280, 96, (1, 1, 0, 0)), (5000, 5000, 96, (1, 1, 0, 0)), (9000, 9000, 256, (1, 1, 0, 0)),
+                                        (4000, 2000, 256, (1, 2, 0, 1)), (2600, 5100, 96, (2, 1, 1, 0)),
+                                        (3000, 1500, 256, (2, 4, 1, 3))])
+def test_dgemm_staircase(ee, m, n, k, grid):
+    """Trailing-update form (eigen_common_2update, src/eigen_t1.F:250-306): C -= A B^T on the tiles that reach
+    the upper staircase of the cyclic local matrix; every element with global row <= global col must be
+    updated, tiles entirely below the staircase must stay untouched (the driver keeps zeros there)."""
+    import torch
+    px, py, x, y = grid
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(m + n + k)
+    A = (torch.rand(k, m, generator=g, dtype=torch.float64) - 0.5).to(dev)
+    B = (torch.rand(k, n, generator=g, dtype=torch.float64) - 0.5).to(dev)
+    C0 = (torch.rand(n, m, generator=g, dtype=torch.float64) - 0.5).to(dev)
+    Cm = C0.clone()
+    torch.cuda.synchronize()
+    ee.dgemm_tri_dev("N", "T", m, n, k, -1.0, A.data_ptr(), m, B.data_ptr(), n, 1.0, Cm.data_ptr(), m, px, py, x, y)
+    ee.sync()
+    ref = C0 - B.T @ A                                    # (n x m) = C^T
+    gr = (torch.arange(m, device=dev) * px + x)[None, :]
+    gc = (torch.arange(n, device=dev) * py + y)[:, None]
+    upper = gr <= gc
+    tol = 4 * (k + 2) * 2.0 ** -52 * float((B.abs().T @ A.abs()).max() + 1.0)
+    assert float(((Cm - ref).abs() * upper).max()) <= tol
+    changed = (Cm != C0)
+    # an element below the staircase may only change together with its whole tile reaching the staircase
+    assert float(((Cm - ref).abs() * changed).max()) <= tol
+    assert int((changed & upper).sum()) >= int(upper.sum()) - m - n     # (exact zeros of the update aside)
