@@ -247,7 +247,11 @@ def main():
     achieved = bytes_rank / symv_s / 1e9 if symv_s > 0 else None
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "symv_ncu_traffic.json"))).get("traffic_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "symv_ncu_traffic.json")))
+        # ncu --set full measured dram bytes / algorithmic bytes of one launch at L ~ N = 50000; the average launch
+        # of this run is smaller by the same factor on both sides
+        traffic_ratio = float(tj["traffic_over_algorithmic"])
+        traffic = traffic_ratio * bytes_rank / n_symv if args.solver == "s" else None
     except Exception:
         pass
     fp64_peak = 35.4
@@ -257,7 +261,9 @@ def main():
         pass
     roofline = {"kernel": "symv2_kernel" if args.solver == "sx" else "symv_kernel", "bound": "hbm", "achieved": achieved,
                 "peak": hbm_peak, "unit": "GB/s",
-                "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic,
+                "traffic_source": "profiles/symv_ncu_traffic.json: dram bytes / algorithmic bytes of one symv launch at N = 50000 "
+                                  "(ncu --set full), scaled to this run's average launch", "peak_source": peak_src,
                 "launches_per_step": n_symv, "avg_launch_ms": symv_s / n_symv * 1e3,
                 "algorithmic_bytes_per_launch_avg": bytes_rank / n_symv,
                 "timing": "CUDA events on the library stream around every launch of the timed steps"}

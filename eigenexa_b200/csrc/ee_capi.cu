@@ -59,8 +59,8 @@ static void pool_configure(int device, bool release_all)
     cudaMemPool_t pool;
     EE_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     if (release_all) { EE_CUDA(cudaMemPoolTrimTo(pool, 0)); return; }
-    // keep up to 48 GB of freed workspace mapped between stages and calls (one N = 50000 matrix is 20 GB)
-    unsigned long long keep = 48ull << 30;
+    // keep up to 64 GB of freed workspace mapped between stages and calls (the D&C of N = 50000 uses 3 x 20 GB)
+    unsigned long long keep = 64ull << 30;
     EE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
 }
 
