@@ -59,8 +59,9 @@ static void pool_configure(int device, bool release_all)
     cudaMemPool_t pool;
     EE_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     if (release_all) { EE_CUDA(cudaMemPoolTrimTo(pool, 0)); return; }
-    // keep up to 64 GB of freed workspace mapped between stages and calls (the D&C of N = 50000 uses 3 x 20 GB)
-    unsigned long long keep = 64ull << 30;
+    // keep freed workspace mapped between stages and calls (N = 50000: 20 GB copies of A and Z, 3 x 20 GB in the
+    // D&C) -- the working set of the next call; eigen_free hands it back
+    unsigned long long keep = ~0ull;
     EE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
 }
 

@@ -1058,6 +1058,23 @@ static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 int trd_lda_pad(int nrl) { return round_up(nrl > 0 ? nrl : 1, TR); }
 int trd_ncl_pad(int ncl) { return round_up(ncl > 0 ? ncl : 1, TC * SW); }
 
+// Internal panel width for wide trailing matrices (even, <= MAXM; EIGENEXA_B200_WIDE_W overrides for tuning).
+// With the cp.async GEMM a K = 256 trailing update paid for a 128-wide panel; the TMA kernel runs K = 96 at
+// nearly the same rate, and the replicated vector kernels cost ~ L x panel width per column, so m_forward
+// itself is used (N = 32000, 1 GPU: eigen_trd 9.00 s at width 48, 9.03 at 64, 9.13 at 96, 9.23 at 128).
+static int wide_panel_width()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("EIGENEXA_B200_WIDE_W");
+        v = e ? atoi(e) : 2;
+        if (v < 2) v = 2;
+        if (v > MAXM) v = MAXM;
+        v -= v % 2;
+    }
+    return v;
+}
+
 void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, int m_forward)
 {
     Context &c = ctx();
@@ -1078,7 +1095,8 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
     // GEMM with K = 2*width; at K = 96 its C read-modify-write (16 B per 4*width flop) is not
     // hidden, so wide trailing matrices use a wider internal panel (same T up to rounding).
     // The panel-internal vector work grows with the width, hence only above WIDE_L.
-    constexpr int WIDE_W = 128, WIDE_L = 16384;
+    const int WIDE_W = wide_panel_width();
+    constexpr int WIDE_L = 16384;
     const int mmax = (n > WIDE_L && m < WIDE_W) ? WIDE_W : m;
 
     // ---- internal padded copy of the local matrix ------------------------------------
@@ -1338,7 +1356,8 @@ void prd_dev(int n, double *a_user, int lda_user, double *d_out, double *e1_out,
     m -= m % 2;                     // the pair loop needs an even width (manual 4.4)
     if (m < 2) m = 2;
     if (m > MAXM) m = MAXM;
-    constexpr int WIDE_W = 128, WIDE_L = 16384;
+    const int WIDE_W = wide_panel_width();
+    constexpr int WIDE_L = 16384;
     const int mmax = (n > WIDE_L && m < WIDE_W) ? WIDE_W : m;
 
     const int lda = trd_lda_pad(nrl), nclp = trd_ncl_pad(ncl);
