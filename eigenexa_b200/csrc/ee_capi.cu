@@ -182,9 +182,13 @@ static void eigen_s_impl(int n, int nvec, double *a, int lda, double *w, double 
     else {
         a_d = (double *)dev_alloc((size_t)ldd * (ncl > 0 ? ncl : 1) * sizeof(double));
         w_d = (double *)dev_alloc((size_t)n * sizeof(double));
-        if (nrl > 0 && ncl > 0)
-            EE_CUDA(cudaMemcpy2DAsync(a_d, (size_t)ldd * sizeof(double), a, (size_t)lda * sizeof(double),
-                                      (size_t)nrl * sizeof(double), ncl, cudaMemcpyHostToDevice, st));
+        if (nrl > 0 && ncl > 0) {
+            // contiguous caller arrays (lda == local rows) go as ONE transfer: a pitched copy of 50000 rows is
+            // issued row by row and does not reach the PCIe rate
+            if (lda == ldd) EE_CUDA(cudaMemcpyAsync(a_d, a, (size_t)ldd * ncl * sizeof(double), cudaMemcpyHostToDevice, st));
+            else EE_CUDA(cudaMemcpy2DAsync(a_d, (size_t)ldd * sizeof(double), a, (size_t)lda * sizeof(double),
+                                           (size_t)nrl * sizeof(double), ncl, cudaMemcpyHostToDevice, st));
+        }
     }
     const int lda_d = dev_ptrs ? lda : ldd;
     double *d_d = (double *)dev_alloc((size_t)n * sizeof(double));
@@ -233,9 +237,11 @@ static void eigen_s_impl(int n, int nvec, double *a, int lda, double *w, double 
                 scale_vec_dev(w_d, n, 1.0 / sigma, st);
             }
             T.mark(4);
-            if (!dev_ptrs && nrl > 0 && nvl > 0)
-                EE_CUDA(cudaMemcpy2DAsync(z, (size_t)ldz * sizeof(double), z_d, (size_t)ldz_d * sizeof(double),
-                                          (size_t)nrl * sizeof(double), nvl, cudaMemcpyDeviceToHost, st));
+            if (!dev_ptrs && nrl > 0 && nvl > 0) {
+                if (ldz == ldz_d) EE_CUDA(cudaMemcpyAsync(z, z_d, (size_t)ldz_d * nvl * sizeof(double), cudaMemcpyDeviceToHost, st));
+                else EE_CUDA(cudaMemcpy2DAsync(z, (size_t)ldz * sizeof(double), z_d, (size_t)ldz_d * sizeof(double),
+                                               (size_t)nrl * sizeof(double), nvl, cudaMemcpyDeviceToHost, st));
+            }
         }
         if (!dev_ptrs) EE_CUDA(cudaMemcpyAsync(w, w_d, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     } else { T.mark(2); T.mark(3); T.mark(4); }

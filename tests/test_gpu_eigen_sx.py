@@ -122,3 +122,54 @@ def test_eigen_sx_mode_n_and_partial(ee):
     assert np.abs(w - wl).max() <= tol
     res, orth = O.ev_test(full, w[:nvec], z)
     assert res <= 10 and orth <= 10
+
+
+def test_eigen_sx_edge_cases(ee):
+    """Same conventions as eigen_s (src/eigen_sx.F:100-131,150-160,284-300): NaN input -> w = NaN, n <= 0 silent,
+    lower triangle never read, odd m_forward rounded to the even width the pair loop needs (manual 4.4),
+    mode 'X' (D&C then bisection refinement), scaling of huge matrices, a(1:3,1) bookkeeping."""
+    n = 60
+    a = O.mat_set(n, 2)
+    full = O.sym_from_upper(a)
+    wl = np.linalg.eigvalsh(full)
+    tol = 10 * n * O.EPS * np.linalg.norm(full)
+    w, z = np.zeros(n), np.zeros((n, n), order="F")
+    bad = F(a); bad[3, 7] = np.nan
+    ee.eigen_sx(n, bad, w, z)
+    assert np.all(np.isnan(w))
+    w[:] = 7.0
+    ee.eigen_sx(0, F(a), w, z)
+    assert np.all(w == 7.0)
+    low = F(a); low[7, 3] = np.nan
+    ee.eigen_sx(n, low, w, z)
+    assert np.abs(w - wl).max() <= tol
+    for mf in (1, 3, 7, 47):
+        ag = F(a)
+        ee.eigen_sx(n, ag, w, z, m_forward=mf, m_backward=5)
+        assert np.abs(w - wl).max() <= tol
+        res, orth = O.ev_test(full, w, z)
+        assert res <= 10 and orth <= 10
+        assert ag[0, 0] > 0 and ag[1, 0] > 0 and ag[2, 0] == -1.0
+    ee.eigen_sx(n, F(a), w, z, mode="X")
+    assert np.abs(w - wl).max() <= tol
+    s = 1e200
+    ee.eigen_sx(n, F(a * s), w, z)
+    assert np.abs(w / s - wl).max() <= tol
+    res, orth = O.ev_test(full, w / s, z)
+    assert res <= 10 and orth <= 10
+
+
+@pytest.mark.parametrize("n", [2000, 3001])
+def test_eigen_sx_spectrum_equals_eigen_s(ee, n):
+    """Both drivers must agree to the eigenvalue bound on the same matrix (different reductions, same spectrum)."""
+    a = O.mat_set(n, 2)
+    full = O.sym_from_upper(a)
+    tol = 10 * n * O.EPS * np.linalg.norm(full)
+    w1, z1 = np.zeros(n), np.zeros((n, n), order="F")
+    w2, z2 = np.zeros(n), np.zeros((n, n), order="F")
+    ee.eigen_s(n, F(a), w1, z1)
+    ee.eigen_sx(n, F(a), w2, z2)
+    assert np.abs(w1 - w2).max() <= tol
+    for (w, z) in ((w1, z1), (w2, z2)):
+        res, orth = O.ev_test(full, w, z)
+        assert res <= 10 and orth <= 10

@@ -1,4 +1,4 @@
-"""Multi-rank parity run (one process per GPU):  torchrun --nproc-per-node P tools/run_multi.py N [mtype]
+"""Multi-rank parity run (one process per GPU):  torchrun --nproc-per-node P tools/run_multi.py N [mtype] [mode] [check|nocheck] [s|sx]
 Each rank builds its 2D-cyclic part, calls eigen_s through the C ABI with host arrays, rank 0 gathers
 w, Z and checks them against the oracle / ev_test.  Prints one JSON line on rank 0."""
 import json, os, sys, time
@@ -12,6 +12,8 @@ from oracle import oracle as O
 n = int(sys.argv[1]); mtype = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 mode = sys.argv[3] if len(sys.argv) > 3 else "A"
 check = (len(sys.argv) <= 4) or sys.argv[4] != "nocheck"
+solver = sys.argv[5] if len(sys.argv) > 5 else "s"
+solve = E.eigen_sx if solver == "sx" else E.eigen_s
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
@@ -22,7 +24,7 @@ nx, ny = E.eigen_get_matdims(n)
 a = O.mat_set_local(n, mtype, px, py, xi, yi, lda=nx, ncols=ny)
 w = np.zeros(n); z = np.zeros((nx, ny), order="F")
 dist.barrier(); t0 = time.perf_counter()
-E.eigen_s(n, a, w, z, mode=mode)
+solve(n, a, w, z, mode=mode)
 dist.barrier(); t1 = time.perf_counter() - t0
 tm = E.last_timings()
 if not check:
