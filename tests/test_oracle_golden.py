@@ -156,3 +156,53 @@ def test_prd_restatement_is_an_orthogonal_band_reduction(n, mt, mf):
     assert res <= 10 and orth <= 10
     if mt == 0:
         assert np.abs(w - O.w_set(n, 0)).max() <= tol
+
+
+def _prd_dense_numpy(full):
+    """Independent statement of the penta-diagonal reduction: for every column pair (c2, c2-1), from the right,
+    apply the two-sided Householder reflections H_a (zeroes A(0:L-1, c2), L = c2-1, pivot row L-1) and then H_b
+    (zeroes A(0:L-2, c2-1), pivot row L-2) to the full dense matrix, with g = -sign(|x|, x_pivot) as
+    src/eigen_prd_t4x.F:262-275 chooses it.  O(n^3) per reflector, for small n only."""
+    a = np.array(full, dtype=np.float64)
+    n = a.shape[0]
+    nrem = 2 + n % 2
+
+    def reflect(col, length):
+        x = a[:length, col].copy()
+        nrm = np.linalg.norm(x)
+        if nrm == 0.0:
+            return
+        g = -np.copysign(nrm, x[-1])
+        u = x.copy(); u[-1] -= g
+        beta = -u[-1] * g
+        h = np.eye(n)
+        h[:length, :length] -= np.outer(u, u) / beta
+        a[:] = h @ a @ h
+
+    c2 = n - 1
+    while c2 >= nrem:
+        L = c2 - 1
+        reflect(c2, L)
+        reflect(c2 - 1, L - 1)
+        c2 -= 2
+    d = np.diag(a).copy()
+    e1 = np.zeros(n); e2 = np.zeros(n)
+    e1[1:] = np.diag(a, 1); e2[2:] = np.diag(a, 2)
+    off = a - O.band_from(d, e1, e2)
+    return d, e1, e2, np.abs(off).max()
+
+
+@pytest.mark.parametrize("n,mf", [(6, 2), (9, 4), (16, 48), (31, 6), (40, 48)])
+def test_prd_restatement_matches_dense_householder_pairs(n, mf):
+    """Pins the blocked C restatement (Cholesky-QR pairs, coupling matrix, panel algebra) against the plain
+    sequence of Householder reflections it must equal (signs included) on a random symmetric matrix."""
+    a = O.mat_set(n, 2)
+    full = O.sym_from_upper(a)
+    dn, e1n, e2n, off = _prd_dense_numpy(full)
+    nrm = np.linalg.norm(full)
+    assert off <= 50 * n * O.EPS * nrm                     # the dense sequence really ends penta-diagonal
+    d, e1, e2 = O.prd(np.array(a, order="F"), mf)
+    tol = 50 * n * O.EPS * nrm
+    assert np.abs(d - dn).max() <= tol
+    assert np.abs(e1 - e1n).max() <= tol
+    assert np.abs(e2 - e2n).max() <= tol
