@@ -19,6 +19,18 @@
 // The eigenvector matrix is never sorted physically between levels; an index permutation is
 // carried on the host and applied once when the caller's cyclic z is written.
 //
+// Memory / multi-GPU layout.  The k x k secular eigenvector matrix is never stored: it is generated in
+// column blocks (<= 2 GB) that go straight into the merge GEMMs, so the work space is two n x n matrices.
+// Two distributions of the eigenvector matrix Q over P ranks:
+//   * replicated (default for P > 1 while 2 n^2 doubles fit comfortably): merges >= 1024 are split by
+//     column slices over the ranks and all-gathered;
+//   * ROW distributed (P = 1 trivially; P > 1 when the replicated form would not fit, or with
+//     EIGENEXA_B200_DC_ROWS=1): rank w owns the rows g = w (mod P).  Every step of the algorithm acts on
+//     rows independently (rotations, column gathers, Q_new(rows,:) = Q_old(rows,:) V) except the four rows
+//     that form z (one small all-reduce per rank-one update); the O(n^2) secular work is replicated, no
+//     eigenvector data moves until the end, where the ranks that share a grid row exchange column sets to
+//     reach the caller's 2D cyclic layout.  Memory per rank: 2 n^2 / P doubles (N = 100000 on 8 GPUs: 20 GB).
+//
 // The same code solves the penta-diagonal matrix of eigen_prd (eigen_dcx, src/dcx.F:75,
 // my_pdsxedc.F, my_pdlaed0.F:226-391): the coupling between the halves of a split at row m is the
 // 2x2 block B = [T(m-2,m) 0 ; T(m-1,m) T(m-1,m+1)], i.e. the sum of two rank-one terms
@@ -47,7 +59,8 @@ constexpr double HALF_EPS = 1.1102230246251565e-16;
 struct LeafDesc { int lo, sz; };
 
 __global__ void __launch_bounds__(32) leaf_jacobi_kernel(const LeafDesc *leaves, const double *d, const double *e,
-                                                         const double *e2, double *Q, long long ldq, double *dout)
+                                                         const double *e2, double *Q, long long ldq, double *dout,
+                                                         int RP, int rw)
 {
     __shared__ double A[LEAF][LEAF + 1];
     __shared__ double V[LEAF][LEAF + 1];
@@ -129,9 +142,13 @@ __global__ void __launch_bounds__(32) leaf_jacobi_kernel(const LeafDesc *leaves,
     }
     __syncwarp();
     if (lane < s) {
-        for (int cdx = 0; cdx < s; cdx++) {
-            int src = order[cdx];
-            Q[(long long)(L.lo + cdx) * ldq + L.lo + lane] = V[lane][src];
+        // row L.lo + lane lives on rank (row mod RP) at local index row / RP
+        if ((L.lo + lane) % RP == rw) {
+            const int jl = (L.lo + lane) / RP;
+            for (int cdx = 0; cdx < s; cdx++) {
+                int src = order[cdx];
+                Q[(long long)(L.lo + cdx) * ldq + jl] = V[lane][src];
+            }
         }
         dout[L.lo + lane] = A[order[lane]][order[lane]];
     }
@@ -139,7 +156,7 @@ __global__ void __launch_bounds__(32) leaf_jacobi_kernel(const LeafDesc *leaves,
 
 // z = Q_node^T w for a vector w with (at most) four non-zeros: rows m-2 .. m+1 around the split
 struct ZSpec { int row[4]; double coef[4]; };
-__global__ void gather_z_kernel(const double *Q, long long ldq, int lo, int ns, ZSpec zs, double *z)
+__global__ void gather_z_kernel(const double *Q, long long ldq, int lo, int ns, ZSpec zs, double *z, int RP, int rw)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= ns) return;
@@ -147,8 +164,8 @@ __global__ void gather_z_kernel(const double *Q, long long ldq, int lo, int ns, 
     double s = 0.0;
 #pragma unroll
     for (int t = 0; t < 4; t++)
-        if (zs.coef[t] != 0.0) s = fma(zs.coef[t], col[zs.row[t]], s);
-    z[j] = s;
+        if (zs.coef[t] != 0.0 && zs.row[t] % RP == rw) s = fma(zs.coef[t], col[zs.row[t] / RP], s);
+    z[j] = s;   // row-distributed: the caller sums the contributions of the owners
 }
 
 struct Rot { int p, q; double c, s; };
@@ -304,11 +321,11 @@ __global__ void __launch_bounds__(128) loewner_kernel(int k, const double *__res
 // column i of the secular eigenvector matrix: V(rowperm[j], i) = z~_j / (d_j - lam_i), normalised
 __global__ void __launch_bounds__(256) secvec_kernel(int k, const double *__restrict__ dl, const double *__restrict__ zt,
                                                      const double *__restrict__ tau, const int *__restrict__ org,
-                                                     const int *__restrict__ rowperm, double *V, long long ldv)
+                                                     const int *__restrict__ rowperm, double *V, long long ldv, int c0)
 {
     __shared__ double sred[8];
     __shared__ double s_inv;
-    const int i = blockIdx.x;
+    const int i = c0 + blockIdx.x;     // columns c0 .. c0 + gridDim.x - 1 of the secular eigenvector matrix
     const double dK = dl[org[i]], ti = tau[i];
     double s = 0.0;
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
@@ -325,7 +342,7 @@ __global__ void __launch_bounds__(256) secvec_kernel(int k, const double *__rest
     }
     __syncthreads();
     const double inv = s_inv;
-    double *col = V + (long long)i * ldv;
+    double *col = V + (long long)blockIdx.x * ldv;
     for (int j = threadIdx.x; j < k; j += blockDim.x) col[rowperm[j]] = zt[j] / ((dl[j] - dK) - ti) * inv;
 }
 
@@ -339,6 +356,29 @@ __global__ void extract_kernel(const double *Q, long long ldq, const int *ord, i
     double *dst = z + (size_t)il * ldz;
     for (int jl = blockIdx.x * blockDim.x + threadIdx.x; jl < nrl; jl += gridDim.x * blockDim.x)
         dst[jl] = src[(long long)jl * px + x];
+}
+
+// row-distributed output, step 1: S_y(jl, il) = Qloc(jl, ord[il*py + y]) for every destination y of the grid row
+__global__ void pack_rows_kernel(const double *Q, long long ldq, const int *ord, int nvec, int py, int nrow, double *S,
+                                 const long long *off)
+{
+    const int c = blockIdx.y;                  // column position 0..nvec-1 in ascending eigenvalue order
+    if (c >= nvec) return;
+    const int y = c % py, il = c / py;
+    const double *src = Q + (long long)ord[c] * ldq;
+    double *dst = S + off[y] + (long long)il * nrow;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrow; r += gridDim.x * blockDim.x) dst[r] = src[r];
+}
+// step 2: z_loc(jl, il) = R_{jl mod py}(jl / py, il); R_y' has nrow(y') rows
+__global__ void unpack_rows_kernel(const double *R, const long long *off, const int *nrows, int py, int nrl, int nvl,
+                                   double *z, int ldz)
+{
+    const int il = blockIdx.y;
+    if (il >= nvl) return;
+    for (int jl = blockIdx.x * blockDim.x + threadIdx.x; jl < nrl; jl += gridDim.x * blockDim.x) {
+        const int ys = jl % py, t = jl / py;
+        z[(size_t)il * ldz + jl] = R[off[ys] + (long long)il * nrows[ys] + t];
+    }
 }
 
 struct Node { int lo, mid, hi; };
@@ -407,17 +447,41 @@ int dc_band_dev(int n, int nvec, const double *d_in, const double *e_in, const d
         tears[t] = tr;
     }
 
-    const long long ldq = ((long long)n + 15) & ~15LL;
+    // ---- distribution of the eigenvector matrix -------------------------------------------------------
+    const int P = g.nnod;
+    bool rows_mode = (P == 1);
+    if (P > 1) {
+        const char *env = getenv("EIGENEXA_B200_DC_ROWS");
+        const double repl_bytes = 4.2 * (double)n * (double)n * sizeof(double);   // Q, Q2, slice + gather buffers
+        if ((env && env[0] == '1') || repl_bytes > 100e9) rows_mode = true;
+        if (env && env[0] == '0') rows_mode = false;
+    }
+    const int RP = rows_mode ? P : 1, rw = rows_mode ? g.inod : 0;     // row partition: row gr on rank gr % RP
+    auto lrows = [&](int gcount) { return cyc_count(gcount, RP, rw); };  // owned rows with global index < gcount
+    const int nrow_loc = lrows(n);
+    // (+4 rows of slack in the distributed form: the final exchange reuses Q / Q2 as receive / send buffers of
+    //  nrl x nvl <= (n/px + 1)(n/py + 1) doubles)
+    const long long ldq = (((long long)(nrow_loc > 0 ? nrow_loc : 1)) + (rows_mode && P > 1 ? 4 : 0) + 15) & ~15LL;
     const size_t qbytes = (size_t)ldq * n * sizeof(double);
     double *Q = (double *)dev_alloc(qbytes);
-    double *Q2 = merges.empty() ? nullptr : (double *)dev_alloc(qbytes);
-    double *Vs = merges.empty() ? nullptr : (double *)dev_alloc(qbytes);
-    // multi-rank merge buffers: this rank's column slice and the gathered block
+    double *Q2 = (merges.empty() && !(rows_mode && P > 1)) ? nullptr : (double *)dev_alloc(qbytes);
+    // secular eigenvectors: generated in column blocks of at most VS_CAP doubles
+    const long long VS_CAP = 1LL << 28;
+    auto block_cols = [&](int k) -> int {
+        if ((long long)(k + 1) * k <= VS_CAP) return k;
+        long long kb = VS_CAP / (k + 1);
+        kb = kb / 64 * 64;
+        return (int)(kb < 64 ? 64 : kb);
+    };
+    const long long vs_doubles = std::min((long long)(n + 1) * n, VS_CAP + (long long)n * 66);
+    double *Vs = merges.empty() ? nullptr : (double *)dev_alloc((size_t)vs_doubles * sizeof(double));
+    // replicated multi-rank merges: this rank's column slice and the gathered block
+    const bool slices = (P > 1) && !rows_mode;
     double *Tb = nullptr, *Gb = nullptr;
-    if (g.nnod > 1 && n >= DIST_MIN) {
-        const size_t sl = (size_t)(((n + g.nnod - 1) / g.nnod + 2) & ~1);
+    if (slices && n >= DIST_MIN) {
+        const size_t sl = (size_t)(((n + P - 1) / P + 2) & ~1);
         Tb = (double *)dev_alloc((size_t)(n + 2) * sl * sizeof(double));
-        Gb = (double *)dev_alloc((size_t)(n + 2) * sl * g.nnod * sizeof(double));
+        Gb = (double *)dev_alloc((size_t)(n + 2) * sl * P * sizeof(double));
     }
     EE_CUDA(cudaMemsetAsync(Q, 0, qbytes, st));
     // small device arrays
@@ -433,8 +497,8 @@ int dc_band_dev(int n, int nvec, const double *d_in, const double *e_in, const d
     if (penta) EE_CUDA(cudaMemcpyAsync(d_e2, he2.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
     EE_CUDA(cudaMemcpyAsync(d_leaves, leaves.data(), sizeof(LeafDesc) * leaves.size(), cudaMemcpyHostToDevice, st));
 
-    // ---- leaves ------------------------------------------------------------------------------
-    leaf_jacobi_kernel<<<(unsigned)leaves.size(), 32, 0, st>>>(d_leaves, d_d, d_e, penta ? d_e2 : nullptr, Q, ldq, d_lam);
+    // ---- leaves (every rank solves all of them, keeps its rows) -----------------------------------------
+    leaf_jacobi_kernel<<<(unsigned)leaves.size(), 32, 0, st>>>(d_leaves, d_d, d_e, penta ? d_e2 : nullptr, Q, ldq, d_lam, RP, rw);
     EE_CHECK_LAUNCH();
     std::vector<double> D(n);  // eigenvalues in physical column order
     EE_CUDA(cudaMemcpyAsync(D.data(), d_lam, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
@@ -448,8 +512,8 @@ int dc_band_dev(int n, int nvec, const double *d_in, const double *e_in, const d
     std::vector<Rot> rots;
 
     double dc_flops = 0.0; long long n_defl_total = 0;
-    // breakdown (seconds): [16] leaves [17] z gather + host deflation [18] rotations + column gather
-    // [19] secular/Loewner/vectors [20] merge GEMMs + deflated copy [21] host sort
+    // breakdown (seconds): [17] z gather + host deflation [18] rotations + column gather
+    // [19] secular/Loewner [20] secular vectors + merge GEMMs + deflated copy [21] host sort
     cudaEvent_t evs[5];
     for (auto &e : evs) EE_CUDA(cudaEventCreate(&e));
     double t_defl = 0, t_perm = 0, t_sec = 0, t_gemm = 0, t_sort = 0;
@@ -460,11 +524,14 @@ int dc_band_dev(int n, int nvec, const double *d_in, const double *e_in, const d
     // children's orders; otherwise it is dense and ord holds the node's own order.
     auto rank_one_update = [&](const Node &m, double rho, const ZSpec &zs, bool blockdiag) {
         const int lo = m.lo, n1 = m.mid - m.lo, ns = m.hi - m.lo, n2 = ns - n1;
-        double *Qb = Q + (long long)lo * ldq + lo, *Q2b = Q2 + (long long)lo * ldq + lo;
+        // local rows of the node: r1 of the upper child, r2 of the lower one
+        const int jl0 = lrows(lo), r1 = lrows(m.mid) - jl0, r2 = lrows(m.hi) - lrows(m.mid), rs = r1 + r2;
+        double *Qb = Q + (long long)lo * ldq + jl0, *Q2b = Q2 + (long long)lo * ldq + jl0;
         double *Dn = D.data() + lo;
         double tw0 = wall();
-        gather_z_kernel<<<(ns + 255) / 256, 256, 0, st>>>(Q, ldq, lo, ns, zs, d_z);
+        gather_z_kernel<<<(ns + 255) / 256, 256, 0, st>>>(Q, ldq, lo, ns, zs, d_z, RP, rw);
         EE_CHECK_LAUNCH();
+        if (RP > 1) comm_allreduce_sum(d_z, (size_t)ns, COMM_WORLD, st);
         EE_CUDA(cudaMemcpyAsync(hz.data(), d_z, sizeof(double) * ns, cudaMemcpyDeviceToHost, st));
         EE_CUDA(cudaStreamSynchronize(st));
         const double isq2 = 1.0 / sqrt(2.0);
@@ -534,15 +601,15 @@ int dc_band_dev(int n, int nvec, const double *d_in, const double *e_in, const d
         t_defl += wall() - tw0;
         // ---- device: rotations, permuted copy, secular system, merge GEMMs ------------
         EE_CUDA(cudaEventRecord(evs[0], st));
-        if (!rots.empty()) {
+        if (!rots.empty() && rs > 0) {
             EE_CUDA(cudaMemcpyAsync(d_rot, rots.data(), sizeof(Rot) * rots.size(), cudaMemcpyHostToDevice, st));
-            apply_rot_kernel<<<(ns + 127) / 128, 128, 0, st>>>(Qb, ldq, ns, d_rot, (int)rots.size());
+            apply_rot_kernel<<<(rs + 127) / 128, 128, 0, st>>>(Qb, ldq, rs, d_rot, (int)rots.size());
             EE_CHECK_LAUNCH();
         }
         EE_CUDA(cudaMemcpyAsync(d_map, map.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, st));
-        {
-            dim3 grid(std::min(16, (ns + 255) / 256), ns);
-            gather_cols_kernel<<<grid, 256, 0, st>>>(Qb, ldq, Q2b, ldq, ns, d_map, ns);
+        if (rs > 0) {
+            dim3 grid(std::min(16, (rs + 255) / 256), ns);
+            gather_cols_kernel<<<grid, 256, 0, st>>>(Qb, ldq, Q2b, ldq, rs, d_map, ns);
             EE_CHECK_LAUNCH();
         }
         const long long ldv = ((long long)k + 1) & ~1LL;
@@ -555,39 +622,46 @@ int dc_band_dev(int n, int nvec, const double *d_in, const double *e_in, const d
         EE_CUDA(cudaMemcpyAsync(lam.data(), d_lam, sizeof(double) * k, cudaMemcpyDeviceToHost, st));
         loewner_kernel<<<k, 128, 0, st>>>(k, d_dl, d_w, d_tau, d_org, d_zt);
         EE_CHECK_LAUNCH();
-        secvec_kernel<<<k, 256, 0, st>>>(k, d_dl, d_zt, d_tau, d_org, d_rowperm, Vs, ldv);
-        EE_CHECK_LAUNCH();
         const int k12 = k1 + k2, k23 = k2 + k3;
         EE_CUDA(cudaEventRecord(evs[2], st));
         n_defl_total += ns - k;
         dc_flops += 2.0 * (double)k * ((double)n1 * k12 + (double)n2 * k23);   // as mx_pdlaed1.F:291,304 counts them
-        if (g.nnod > 1 && ns >= DIST_MIN && k >= 2 * g.nnod) {
-            // multi-rank: every rank forms its slice of the k merged columns, then one
-            // all-gather puts the whole block on every rank (everything else is replicated, so
-            // all ranks take identical deflation decisions in the next level)
-            const int P = g.nnod;
+        // new columns [c0, c1) produced by this rank into dst (ld ldd): secular vectors of a column block,
+        // then  top rows = Q2(0:r1, 0:k12) V(0:k12, blk)  and  bottom rows = Q2(r1:, k1:k) V(k1:k, blk)
+        auto produce = [&](int c0, int c1, double *dst, long long ldd) {
+            const int kbmax = block_cols(k);
+            for (int cb = c0; cb < c1; cb += kbmax) {
+                const int kb = std::min(kbmax, c1 - cb);
+                secvec_kernel<<<kb, 256, 0, st>>>(k, d_dl, d_zt, d_tau, d_org, d_rowperm, Vs, ldv, cb);
+                EE_CHECK_LAUNCH();
+                double *dcol = dst + (long long)(cb - c0) * ldd;
+                if (r1 > 0) {
+                    if (k12 > 0) dgemm_ex(st, 'N', 'N', r1, kb, k12, 1.0, Q2b, ldq, Vs, ldv, 0.0, dcol, ldd, 1, 0);
+                    else EE_CUDA(cudaMemset2DAsync(dcol, ldd * sizeof(double), 0, (size_t)r1 * sizeof(double), kb, st));
+                }
+                if (r2 > 0) {
+                    if (k23 > 0) dgemm_ex(st, 'N', 'N', r2, kb, k23, 1.0, Q2b + r1 + (long long)k1 * ldq, ldq, Vs + k1, ldv, 0.0, dcol + r1, ldd, 1, 0);
+                    else EE_CUDA(cudaMemset2DAsync(dcol + r1, ldd * sizeof(double), 0, (size_t)r2 * sizeof(double), kb, st));
+                }
+            }
+        };
+        if (slices && ns >= DIST_MIN && k >= 2 * P) {
+            // replicated Q: every rank forms its slice of the k merged columns, then one all-gather puts the
+            // whole block on every rank (everything else is replicated, so all ranks take identical
+            // deflation decisions in the next level)
             int slice = ((k + P - 1) / P + 1) & ~1;
             const long long ldt = ((long long)ns + 1) & ~1LL;
             const int c0 = std::min(k, g.inod * slice), c1 = std::min(k, c0 + slice);
-            const int wdt = c1 - c0;
-            if (wdt > 0) {
-                if (k12 > 0) dgemm_ex(st, 'N', 'N', n1, wdt, k12, 1.0, Q2b, ldq, Vs + (long long)c0 * ldv, ldv, 0.0, Tb, ldt, 1, 0);
-                else EE_CUDA(cudaMemset2DAsync(Tb, ldt * sizeof(double), 0, (size_t)n1 * sizeof(double), wdt, st));
-                if (k23 > 0) dgemm_ex(st, 'N', 'N', n2, wdt, k23, 1.0, Q2b + n1 + (long long)k1 * ldq, ldq, Vs + k1 + (long long)c0 * ldv, ldv, 0.0, Tb + n1, ldt, 1, 0);
-                else EE_CUDA(cudaMemset2DAsync(Tb + n1, ldt * sizeof(double), 0, (size_t)n2 * sizeof(double), wdt, st));
-            }
+            if (c1 > c0) produce(c0, c1, Tb, ldt);
             comm_allgather(Tb, Gb, (size_t)ldt * slice, COMM_WORLD, st);
             EE_CUDA(cudaMemcpy2DAsync(Qb, ldq * sizeof(double), Gb, ldt * sizeof(double), (size_t)ns * sizeof(double), k,
                                       cudaMemcpyDeviceToDevice, st));
         } else {
-        if (k12 > 0) dgemm_ex(st, 'N', 'N', n1, k, k12, 1.0, Q2b, ldq, Vs, ldv, 0.0, Qb, ldq, 1, 0);
-        else EE_CUDA(cudaMemset2DAsync(Qb, ldq * sizeof(double), 0, (size_t)n1 * sizeof(double), k, st));
-        if (k23 > 0) dgemm_ex(st, 'N', 'N', n2, k, k23, 1.0, Q2b + n1 + (long long)k1 * ldq, ldq, Vs + k1, ldv, 0.0, Qb + n1, ldq, 1, 0);
-        else EE_CUDA(cudaMemset2DAsync(Qb + n1, ldq * sizeof(double), 0, (size_t)n2 * sizeof(double), k, st));
+            produce(0, k, Qb, ldq);
         }
-        if (ns > k)
+        if (ns > k && rs > 0)
             EE_CUDA(cudaMemcpy2DAsync(Qb + (long long)k * ldq, ldq * sizeof(double), Q2b + (long long)k * ldq, ldq * sizeof(double),
-                                      (size_t)ns * sizeof(double), ns - k, cudaMemcpyDeviceToDevice, st));
+                                      (size_t)rs * sizeof(double), ns - k, cudaMemcpyDeviceToDevice, st));
         EE_CUDA(cudaEventRecord(evs[3], st));
         EE_CUDA(cudaStreamSynchronize(st));
         {
@@ -609,8 +683,6 @@ int dc_band_dev(int n, int nvec, const double *d_in, const double *e_in, const d
         }
         t_sort += wall() - tw1;
     };
-    const double SQ2 = sqrt(2.0);
-    (void)SQ2;
     for (size_t t = 0; t < merges.size(); t++) {
         const Node &m = merges[t];
         const Tear &tr = tears[t];
@@ -648,10 +720,58 @@ int dc_band_dev(int n, int nvec, const double *d_in, const double *e_in, const d
         for (int i = 0; i < n; i++) wv[i] = D[ord[i]];
         EE_CUDA(cudaMemcpyAsync(w_out, wv.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
         EE_CUDA(cudaMemcpyAsync(d_ord, ord.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
-        if (nrl > 0 && nvl > 0) {
-            dim3 grid(std::min(16, (nrl + 255) / 256), nvl);
-            extract_kernel<<<grid, 256, 0, st>>>(Q, ldq, d_ord, n, nvec, g.px, g.py, g.x, g.y, z, ldz, nrl, nvl);
-            EE_CHECK_LAUNCH();
+        if (!(rows_mode && P > 1)) {
+            // the rank holds every row it needs
+            if (nrl > 0 && nvl > 0) {
+                dim3 grid(std::min(16, (nrl + 255) / 256), nvl);
+                extract_kernel<<<grid, 256, 0, st>>>(Q, ldq, d_ord, n, nvec, g.px, g.py, g.x, g.y, z, ldz, nrl, nvl);
+                EE_CHECK_LAUNCH();
+            }
+        } else {
+            // Row-distributed: rank (x, y') owns the rows g = x + y' px (mod P), i.e. the local rows jl = y' (mod py)
+            // of grid row x.  Pack, for every rank (x, y) of the grid row, the columns it owns (position c = y mod py
+            // in ascending order), exchange inside the grid row, interleave the received row sets.
+            const int px = g.px, py = g.py;
+            std::vector<long long> soff(py + 1, 0), roff(py + 1, 0);
+            std::vector<int> nrows(py, 0);
+            for (int y = 0; y < py; y++) {
+                soff[y + 1] = soff[y] + (long long)nrow_loc * cyc_count(nvec, py, y);
+                nrows[y] = cyc_count(n, P, g.x + y * px);
+                roff[y + 1] = roff[y] + (long long)nrows[y] * nvl;
+            }
+            if (soff[py] > (long long)ldq * n || roff[py] > (long long)ldq * n)
+                fatal("dc: exchange buffers exceed the eigenvector work space", __FILE__, __LINE__);
+            long long *d_off = (long long *)dev_alloc(sizeof(long long) * 2 * (py + 1));
+            int *d_nrows = (int *)dev_alloc(sizeof(int) * py);
+            EE_CUDA(cudaMemcpyAsync(d_off, soff.data(), sizeof(long long) * (py + 1), cudaMemcpyHostToDevice, st));
+            EE_CUDA(cudaMemcpyAsync(d_off + py + 1, roff.data(), sizeof(long long) * (py + 1), cudaMemcpyHostToDevice, st));
+            EE_CUDA(cudaMemcpyAsync(d_nrows, nrows.data(), sizeof(int) * py, cudaMemcpyHostToDevice, st));
+            if (nrow_loc > 0 && nvec > 0) {
+                dim3 grid(std::min(16, (nrow_loc + 255) / 256), nvec);
+                pack_rows_kernel<<<grid, 256, 0, st>>>(Q, ldq, d_ord, nvec, py, nrow_loc, Q2, d_off);
+                EE_CHECK_LAUNCH();
+            }
+            // Q is free now: it receives the row sets of the grid row
+            comm_group_start();
+            for (int y = 0; y < py; y++) {
+                if (y == g.y) continue;
+                const int peer = g.x + y * px;
+                const size_t scount = (size_t)(soff[y + 1] - soff[y]), rcount = (size_t)(roff[y + 1] - roff[y]);
+                if (scount) comm_send(Q2 + soff[y], scount, peer, st);
+                if (rcount) comm_recv(Q + roff[y], rcount, peer, st);
+            }
+            comm_group_end();
+            {
+                const size_t self = (size_t)(soff[g.y + 1] - soff[g.y]);
+                if (self) EE_CUDA(cudaMemcpyAsync(Q + roff[g.y], Q2 + soff[g.y], self * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            }
+            if (nrl > 0 && nvl > 0) {
+                dim3 grid(std::min(16, (nrl + 255) / 256), nvl);
+                unpack_rows_kernel<<<grid, 256, 0, st>>>(Q, d_off + py + 1, d_nrows, py, nrl, nvl, z, ldz);
+                EE_CHECK_LAUNCH();
+            }
+            EE_CUDA(cudaStreamSynchronize(st));
+            dev_free(d_off); dev_free(d_nrows);
         }
         EE_CUDA(cudaStreamSynchronize(st));
     }
