@@ -1,4 +1,7 @@
-// ee_trd.cu -- blocked Householder tridiagonalisation on B200 (sm_100a).
+// ee_trd.cu -- blocked Householder tri- and penta-diagonalisation on B200 (sm_100a).
+//
+// eigen_prd (two columns per step, src/eigen_prd.F) shares the SYMV tile kernel, the panel kernels and the
+// trailing update with eigen_trd; its own kernels and their algebra are described further down.
 //
 // Replaces eigen_trd and its helpers (reference: src/eigen_trd.F:82-723,
 // src/eigen_trd_t2.F (au: SYMV + scalars), _t4 (compute_u), _t5/_t5x (panel update),
