@@ -66,3 +66,41 @@ def test_two_rank_host_logic(world):
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) == "ok"
+
+
+@pytest.mark.parametrize("px,py,n,nvec", [(1, 2, 37, 37), (2, 2, 50, 41), (2, 4, 101, 101), (1, 8, 64, 50), (3, 2, 45, 45), (2, 4, 9, 9)])
+def test_row_distributed_dc_exchange_algebra(px, py, n, nvec):
+    """Index algebra of the row-distributed divide & conquer's last step (ee_dc.cu: pack_rows_kernel, grouped
+    send/recv inside a grid row, unpack_rows_kernel), restated in numpy for grids the GPU tests cannot reach:
+    world rank w = x + y*px owns the rows g = w (mod P) at local index g // P; rank (x, y) must end up with
+    Z(jl, il) = Q(jl*px + x, ord[il*py + y]) -- the 2D cyclic layout of src/eigen_libs0.F:1986-2166."""
+    rng = np.random.default_rng(px * 100 + py * 10 + n)
+    P = px * py
+    Q = rng.standard_normal((n, n))
+    ordv = rng.permutation(n)
+    cyc = lambda G, Pn, r: (G - r + Pn - 1) // Pn if G > r else 0
+    # what every rank holds before the exchange
+    loc = {w: Q[w::P, :] for w in range(P)}
+    for x in range(px):
+        # pack on every sender (x, ys): one buffer per destination y of the grid row, column-major (row fastest)
+        send = {}
+        for ys in range(py):
+            w = x + ys * px
+            nrow = loc[w].shape[0]
+            assert nrow == cyc(n, P, w)
+            for y in range(py):
+                cols = [ordv[il * py + y] for il in range(cyc(nvec, py, y))]
+                send[(ys, y)] = loc[w][:, cols]                       # (nrow, nvl_y)
+        # unpack on every receiver (x, y)
+        for y in range(py):
+            nrl, nvl = cyc(n, px, x), cyc(nvec, py, y)
+            z = np.zeros((nrl, nvl))
+            for jl in range(nrl):
+                ys, t = jl % py, jl // py
+                z[jl, :] = send[(ys, y)][t, :]
+            want = np.array([[Q[jl * px + x, ordv[il * py + y]] for il in range(nvl)] for jl in range(nrl)]).reshape(nrl, nvl)
+            assert np.array_equal(z, want)
+            # buffer sizes the driver checks: receive side fits into (nrow_loc + 4 rounded to 16) * n doubles
+            nrow_loc = cyc(n, P, x + y * px)
+            ldq = (max(nrow_loc, 1) + 4 + 15) // 16 * 16
+            assert nrl * nvl <= ldq * n
