@@ -173,3 +173,36 @@ def test_eigen_sx_spectrum_equals_eigen_s(ee, n):
     for (w, z) in ((w1, z1), (w2, z2)):
         res, orth = O.ev_test(full, w, z)
         assert res <= 10 and orth <= 10
+
+
+@pytest.mark.parametrize("solver", ["s", "sx"])
+@pytest.mark.parametrize("kind", ["zero", "identity", "diag", "repeated_blocks", "rank_one", "arrow"])
+def test_degenerate_matrices(ee, solver, kind):
+    """sigma = 0 columns (g = 0, u = 0, beta = 1: src/eigen_trd_t2.F:574-583, src/eigen_prd_t4x.F:204-215), total
+    deflation in the divide & conquer, multiple eigenvalues: no NaN, spectrum and eigenvector gates hold."""
+    n = 130
+    rng = np.random.default_rng(7)
+    if kind == "zero":
+        full = np.zeros((n, n))
+    elif kind == "identity":
+        full = np.eye(n)
+    elif kind == "diag":
+        full = np.diag(np.repeat(np.arange(1.0, 14.0), 10))
+    elif kind == "repeated_blocks":
+        b = rng.standard_normal((10, 10)); b = b + b.T
+        full = np.kron(np.eye(13), b)
+    elif kind == "rank_one":
+        v = rng.standard_normal(n)
+        full = np.outer(v, v)
+    else:
+        full = np.diag(np.arange(1.0, n + 1.0))
+        full[:, -1] = 1.0; full[-1, :] = 1.0; full[-1, -1] = 5.0
+    a = np.asfortranarray(np.triu(full))
+    w, z = np.zeros(n), np.zeros((n, n), order="F")
+    (ee.eigen_sx if solver == "sx" else ee.eigen_s)(n, a, w, z)
+    assert np.all(np.isfinite(w)) and np.all(np.isfinite(z))
+    nrm = max(np.linalg.norm(full), 1.0)
+    assert np.abs(w - np.linalg.eigvalsh(full)).max() <= 10 * n * O.EPS * nrm
+    r = full @ z - z * w[None, :]
+    assert np.linalg.norm(r) <= 10 * n * O.EPS * nrm
+    assert np.linalg.norm(z.T @ z - np.eye(n)) <= 10 * n * O.EPS
