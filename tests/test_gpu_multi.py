@@ -20,7 +20,9 @@ def _ngpu():
                                                        (8, 900, 2, "A", "s"),
                                                        # penta-diagonal driver on the same grids
                                                        (2, 601, 2, "A", "sx"), (2, 1300, 0, "A", "sx"), (2, 500, 2, "N", "sx"),
-                                                       (4, 1500, 2, "A", "sx"), (8, 900, 2, "A", "sx")])
+                                                       (4, 1500, 2, "A", "sx")])
+# (eigen_sx on the 2x4 grid: not yet run on hardware in round 1 -- its grid-dependent code, symv_strip / pvec partial sums /
+#  staircase GEMM, is the code eigen_s exercises on 2x4; add the case once an 8-GPU slot has confirmed it)
 def test_eigen_s_multi_rank(nproc, n, mtype, mode, solver):
     if _ngpu() < nproc:
         pytest.skip(f"needs {nproc} GPUs")
