@@ -186,11 +186,11 @@ __global__ void apply_rot_kernel(double *Qb, long long ldq, int ns, const Rot *r
 __global__ void gather_cols_kernel(const double *src, long long lds, double *dst, long long ldd, int rows,
                                    const int *map, int ncols)
 {
-    int c = blockIdx.y;
-    if (c >= ncols) return;
-    const double *s = src + (long long)map[c] * lds;
-    double *d = dst + (long long)c * ldd;
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) d[r] = s[r];
+    for (int c = blockIdx.y; c < ncols; c += gridDim.y) {     // gridDim.y is capped at 32768 by the callers
+        const double *s = src + (long long)map[c] * lds;
+        double *d = dst + (long long)c * ldd;
+        for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) d[r] = s[r];
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -350,35 +350,34 @@ __global__ void __launch_bounds__(256) secvec_kernel(int k, const double *__rest
 __global__ void extract_kernel(const double *Q, long long ldq, const int *ord, int n, int nvec, int px, int py, int x,
                                int y, double *z, int ldz, int nrl, int nvl)
 {
-    int il = blockIdx.y;
-    if (il >= nvl) return;
-    const double *src = Q + (long long)ord[il * py + y] * ldq;
-    double *dst = z + (size_t)il * ldz;
-    for (int jl = blockIdx.x * blockDim.x + threadIdx.x; jl < nrl; jl += gridDim.x * blockDim.x)
-        dst[jl] = src[(long long)jl * px + x];
+    for (int il = blockIdx.y; il < nvl; il += gridDim.y) {
+        const double *src = Q + (long long)ord[il * py + y] * ldq;
+        double *dst = z + (size_t)il * ldz;
+        for (int jl = blockIdx.x * blockDim.x + threadIdx.x; jl < nrl; jl += gridDim.x * blockDim.x)
+            dst[jl] = src[(long long)jl * px + x];
+    }
 }
 
 // row-distributed output, step 1: S_y(jl, il) = Qloc(jl, ord[il*py + y]) for every destination y of the grid row
 __global__ void pack_rows_kernel(const double *Q, long long ldq, const int *ord, int nvec, int py, int nrow, double *S,
                                  const long long *off)
 {
-    const int c = blockIdx.y;                  // column position 0..nvec-1 in ascending eigenvalue order
-    if (c >= nvec) return;
-    const int y = c % py, il = c / py;
-    const double *src = Q + (long long)ord[c] * ldq;
-    double *dst = S + off[y] + (long long)il * nrow;
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrow; r += gridDim.x * blockDim.x) dst[r] = src[r];
+    for (int c = blockIdx.y; c < nvec; c += gridDim.y) {   // column position in ascending eigenvalue order
+        const int y = c % py, il = c / py;
+        const double *src = Q + (long long)ord[c] * ldq;
+        double *dst = S + off[y] + (long long)il * nrow;
+        for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrow; r += gridDim.x * blockDim.x) dst[r] = src[r];
+    }
 }
 // step 2: z_loc(jl, il) = R_{jl mod py}(jl / py, il); R_y' has nrow(y') rows
 __global__ void unpack_rows_kernel(const double *R, const long long *off, const int *nrows, int py, int nrl, int nvl,
                                    double *z, int ldz)
 {
-    const int il = blockIdx.y;
-    if (il >= nvl) return;
-    for (int jl = blockIdx.x * blockDim.x + threadIdx.x; jl < nrl; jl += gridDim.x * blockDim.x) {
-        const int ys = jl % py, t = jl / py;
-        z[(size_t)il * ldz + jl] = R[off[ys] + (long long)il * nrows[ys] + t];
-    }
+    for (int il = blockIdx.y; il < nvl; il += gridDim.y)
+        for (int jl = blockIdx.x * blockDim.x + threadIdx.x; jl < nrl; jl += gridDim.x * blockDim.x) {
+            const int ys = jl % py, t = jl / py;
+            z[(size_t)il * ldz + jl] = R[off[ys] + (long long)il * nrows[ys] + t];
+        }
 }
 
 struct Node { int lo, mid, hi; };
@@ -608,7 +607,7 @@ int dc_band_dev(int n, int nvec, const double *d_in, const double *e_in, const d
         }
         EE_CUDA(cudaMemcpyAsync(d_map, map.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, st));
         if (rs > 0) {
-            dim3 grid(std::min(16, (rs + 255) / 256), ns);
+            dim3 grid(std::min(16, (rs + 255) / 256), std::min(ns, 32768));
             gather_cols_kernel<<<grid, 256, 0, st>>>(Qb, ldq, Q2b, ldq, rs, d_map, ns);
             EE_CHECK_LAUNCH();
         }
@@ -723,7 +722,7 @@ int dc_band_dev(int n, int nvec, const double *d_in, const double *e_in, const d
         if (!(rows_mode && P > 1)) {
             // the rank holds every row it needs
             if (nrl > 0 && nvl > 0) {
-                dim3 grid(std::min(16, (nrl + 255) / 256), nvl);
+                dim3 grid(std::min(16, (nrl + 255) / 256), std::min(nvl, 32768));
                 extract_kernel<<<grid, 256, 0, st>>>(Q, ldq, d_ord, n, nvec, g.px, g.py, g.x, g.y, z, ldz, nrl, nvl);
                 EE_CHECK_LAUNCH();
             }
@@ -747,7 +746,7 @@ int dc_band_dev(int n, int nvec, const double *d_in, const double *e_in, const d
             EE_CUDA(cudaMemcpyAsync(d_off + py + 1, roff.data(), sizeof(long long) * (py + 1), cudaMemcpyHostToDevice, st));
             EE_CUDA(cudaMemcpyAsync(d_nrows, nrows.data(), sizeof(int) * py, cudaMemcpyHostToDevice, st));
             if (nrow_loc > 0 && nvec > 0) {
-                dim3 grid(std::min(16, (nrow_loc + 255) / 256), nvec);
+                dim3 grid(std::min(16, (nrow_loc + 255) / 256), std::min(nvec, 32768));
                 pack_rows_kernel<<<grid, 256, 0, st>>>(Q, ldq, d_ord, nvec, py, nrow_loc, Q2, d_off);
                 EE_CHECK_LAUNCH();
             }
@@ -766,7 +765,7 @@ int dc_band_dev(int n, int nvec, const double *d_in, const double *e_in, const d
                 if (self) EE_CUDA(cudaMemcpyAsync(Q + roff[g.y], Q2 + soff[g.y], self * sizeof(double), cudaMemcpyDeviceToDevice, st));
             }
             if (nrl > 0 && nvl > 0) {
-                dim3 grid(std::min(16, (nrl + 255) / 256), nvl);
+                dim3 grid(std::min(16, (nrl + 255) / 256), std::min(nvl, 32768));
                 unpack_rows_kernel<<<grid, 256, 0, st>>>(Q, d_off + py + 1, d_nrows, py, nrl, nvl, z, ldz);
                 EE_CHECK_LAUNCH();
             }

@@ -42,28 +42,28 @@ __host__ __device__ inline double mat_elem(int mtype, int n, int j, int i, uint6
 __global__ void mat_set_kernel(int n, double *a, int lda, int mtype, uint64_t seed, int px, int py, int x, int y, int nrl,
                                int ncl)
 {
-    const int il = blockIdx.y;
     const int jl = blockIdx.x * blockDim.x + threadIdx.x;
-    if (jl >= nrl || il >= ncl) return;
-    const int gj = jl * px + x + 1, gi = il * py + y + 1;
-    a[(size_t)il * lda + jl] = mat_elem(mtype, n, gj, gi, seed);
+    if (jl >= nrl) return;
+    for (int il = blockIdx.y; il < ncl; il += gridDim.y) {     // gridDim.y is capped at 32768 by the callers
+        const int gj = jl * px + x + 1, gi = il * py + y + 1;
+        a[(size_t)il * lda + jl] = mat_elem(mtype, n, gj, gi, seed);
+    }
 }
 
 __global__ void symmetrize_kernel(int n, const double *a, int lda, double *full, int ldf)
 {
-    const int i = blockIdx.y;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    full[(size_t)i * ldf + j] = (j <= i) ? a[(size_t)i * lda + j] : a[(size_t)j * lda + i];
+    for (int i = blockIdx.y; i < n; i += gridDim.y)
+        full[(size_t)i * ldf + j] = (j <= i) ? a[(size_t)i * lda + j] : a[(size_t)j * lda + i];
 }
 
 // r(:, c) -= w[c] * z(:, c)
 __global__ void sub_zw_kernel(int n, int nv, double *r, int ldr, const double *z, int ldz, const double *w)
 {
-    const int c = blockIdx.y;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n || c >= nv) return;
-    r[(size_t)c * ldr + j] -= w[c] * z[(size_t)c * ldz + j];
+    if (j >= n) return;
+    for (int c = blockIdx.y; c < nv; c += gridDim.y) r[(size_t)c * ldr + j] -= w[c] * z[(size_t)c * ldz + j];
 }
 __global__ void sub_eye_kernel(int nv, double *g, int ldg)
 {
@@ -102,7 +102,7 @@ void mat_set_dev(int n, double *a, int lda, int mtype, uint64_t seed)
     const Grid &g = c.g;
     const int nrl = cyc_count(n, g.px, g.x), ncl = cyc_count(n, g.py, g.y);
     if (nrl <= 0 || ncl <= 0) return;
-    dim3 grid((nrl + 255) / 256, ncl);
+    dim3 grid((nrl + 255) / 256, std::min(ncl, 32768));
     mat_set_kernel<<<grid, 256, 0, c.stream>>>(n, a, lda, mtype, seed, g.px, g.py, g.x, g.y, nrl, ncl);
     EE_CHECK_LAUNCH();
 }
@@ -136,12 +136,12 @@ void ev_test_dev(int n, int nvec, const double *a, int lda, const double *w, con
     double *full = (double *)dev_alloc((size_t)ldf * n * sizeof(double));
     double *r = (double *)dev_alloc((size_t)ldf * nvec * sizeof(double));
     double *scr = (double *)dev_alloc(64);
-    dim3 grid((n + 255) / 256, n);
+    dim3 grid((n + 255) / 256, std::min(n, 32768));
     symmetrize_kernel<<<grid, 256, 0, st>>>(n, a, lda, full, ldf);
     EE_CHECK_LAUNCH();
     const double anorm = sqrt(fro2(st, n, n, full, ldf, scr));
     dgemm(st, 'N', 'N', n, nvec, n, 1.0, full, ldf, z, ldz, 0.0, r, ldf);
-    dim3 grid2((n + 255) / 256, nvec);
+    dim3 grid2((n + 255) / 256, std::min(nvec, 32768));
     sub_zw_kernel<<<grid2, 256, 0, st>>>(n, nvec, r, ldf, z, ldz, w);
     EE_CHECK_LAUNCH();
     const double err1 = sqrt(fro2(st, n, nvec, r, ldf, scr));

@@ -607,11 +607,12 @@ __global__ void trd_final_store_kernel(TrdP P)
 // zero the strictly lower part and the padding of the local matrix (trd_t8.F:84-94)
 __global__ void zero_lower_kernel(double *A, int lda, int ncols, int n, int px, int py, int x, int y)
 {
-    const int il = blockIdx.y;
     const int jl = blockIdx.x * blockDim.x + threadIdx.x;
-    if (jl >= lda || il >= ncols) return;
-    long long gr = (long long)jl * px + x, gc = (long long)il * py + y;
-    if (gr > gc || gr >= n || gc >= n) A[(size_t)il * lda + jl] = 0.0;
+    if (jl >= lda) return;
+    for (int il = blockIdx.y; il < ncols; il += gridDim.y) {   // gridDim.y is capped at 32768 by the callers
+        long long gr = (long long)jl * px + x, gc = (long long)il * py + y;
+        if (gr > gc || gr >= n || gc >= n) A[(size_t)il * lda + jl] = 0.0;
+    }
 }
 
 // max |a| over the upper triangle + non-finite flag (eigen_scaling.F:92-107)
@@ -641,11 +642,12 @@ __global__ void absmax_kernel(const double *A, int lda, int n, int px, int py, i
 }
 __global__ void scale_upper_kernel(double *A, int lda, int n, int px, int py, int x, int y, int nrl, int ncl, double s)
 {
-    const int il = blockIdx.y;
     const int jl = blockIdx.x * blockDim.x + threadIdx.x;
-    if (jl >= nrl || il >= ncl) return;
-    long long gr = (long long)jl * px + x, gc = (long long)il * py + y;
-    if (gr <= gc) A[(size_t)il * lda + jl] *= s;
+    if (jl >= nrl) return;
+    for (int il = blockIdx.y; il < ncl; il += gridDim.y) {
+        long long gr = (long long)jl * px + x, gc = (long long)il * py + y;
+        if (gr <= gc) A[(size_t)il * lda + jl] *= s;
+    }
 }
 
 // =========================================================================================
@@ -1049,7 +1051,7 @@ double scaling_dev(int n, double *a, int lda)
     if (anrm != 0.0 && anrm < RMIN) sigma = RMIN / anrm;
     else if (anrm > RMAX) sigma = RMAX / anrm;
     if (sigma != 1.0 && nrl > 0 && ncl > 0) {
-        dim3 grid((nrl + 255) / 256, ncl);
+        dim3 grid((nrl + 255) / 256, std::min(ncl, 32768));
         scale_upper_kernel<<<grid, 256, 0, c.stream>>>(a, lda, n, g.px, g.py, g.x, g.y, nrl, ncl, sigma);
         EE_CHECK_LAUNCH();
     }
@@ -1110,7 +1112,7 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
         EE_CUDA(cudaMemcpy2DAsync(A, (size_t)lda * sizeof(double), a_user, (size_t)lda_user * sizeof(double),
                                   (size_t)nrl * sizeof(double), ncl, cudaMemcpyDeviceToDevice, st));
     {
-        dim3 grid((lda + 255) / 256, nclp);
+        dim3 grid((lda + 255) / 256, std::min(nclp, 32768));
         zero_lower_kernel<<<grid, 256, 0, st>>>(A, lda, nclp, n, g.px, g.py, g.x, g.y);
         EE_CHECK_LAUNCH();
     }
@@ -1370,7 +1372,7 @@ void prd_dev(int n, double *a_user, int lda_user, double *d_out, double *e1_out,
         EE_CUDA(cudaMemcpy2DAsync(A, (size_t)lda * sizeof(double), a_user, (size_t)lda_user * sizeof(double),
                                   (size_t)nrl * sizeof(double), ncl, cudaMemcpyDeviceToDevice, st));
     {
-        dim3 grid((lda + 255) / 256, nclp);
+        dim3 grid((lda + 255) / 256, std::min(nclp, 32768));
         zero_lower_kernel<<<grid, 256, 0, st>>>(A, lda, nclp, n, g.px, g.py, g.x, g.y);
         EE_CHECK_LAUNCH();
     }
