@@ -62,3 +62,28 @@ def test_version_and_uninitialised_calls_are_silent():
     E.eigen_s(n, a, w, z)
     assert np.all(w == 7.0)
     E.eigen_free()  # no-op when not initialised
+
+
+def test_no_gpu_means_loud_failure_not_cpu_fallback():
+    """On a box without a CUDA device eigen_init must report the missing device (there is no CPU path), and the
+    stage-level entry points must refuse to run instead of computing anything on the host."""
+    import torch
+    import pytest
+    import eigenexa_b200 as E
+    if torch.cuda.is_available():
+        pytest.skip("this check is for CPU-only boxes")
+    E.eigen_init(None, "C")
+    assert "no CUDA device" in E.last_error() and "no CPU fallback" in E.last_error()
+    assert E.eigen_get_procs()[0] in (0, 1)
+    n = 8
+    a = np.asfortranarray(np.eye(n))
+    for call in (lambda: E.eigen_trd(n, a.copy(order="F")), lambda: E.eigen_prd(n, a.copy(order="F")),
+                 lambda: E.eigen_dc(n, np.ones(n), np.zeros(n), np.zeros((n, n), order="F")),
+                 lambda: E.eigen_bisect(n, np.ones(n), np.zeros(n)),
+                 lambda: E.eigen_bisect2(n, np.ones(n), np.zeros(n), np.zeros(n))):
+        with pytest.raises(RuntimeError):
+            call()
+    # the drivers return silently like the reference does without eigen_init (src/eigen_s.F:81-84)
+    w = np.full(n, 3.0); z = np.zeros((n, n), order="F")
+    E.eigen_sx(n, a.copy(order="F"), w, z)
+    assert np.all(w == 3.0)
