@@ -1147,7 +1147,8 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
     const bool multi = g.nnod > 1;
     PeerView pv;
     memset(&pv, 0, sizeof pv);
-    const bool use_peer = multi && comm_peer_setup((size_t)npad, &pv);
+    // (two vectors per slot, as eigen_prd needs: a later eigen_sx of the same size then reuses the ring as it is)
+    const bool use_peer = multi && comm_peer_setup((size_t)2 * npad, &pv);
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float t_symv = 0.f, t_syr2k = 0.f, t_pvec = 0.f, t_vvec = 0.f;
