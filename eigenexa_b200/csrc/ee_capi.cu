@@ -442,6 +442,87 @@ void eigen_libs0_eigen_get_procs_(int *a, int *b, int *c2) { eigen_get_procs(a, 
 void eigen_libs0_eigen_get_id_(int *a, int *b, int *c2) { eigen_get_id(a, b, c2); }
 void eigen_libs0_eigen_get_errinfo_(int *info) { eigen_get_errinfo(info); }
 
+// ---- remaining symbols of C/eigen_exa_interfaces.h:3-33 and C/EigenExa.h:40 ---------------------
+// eigen_show_version (src/eigen_libs0.F:207-236): banner on the first rank of the grid
+void eigen_show_version(void)
+{
+    int v; char date[64], vcode[64];
+    eigen_get_version(&v, date, vcode);
+    if (ctx().g.inod == 0)
+        printf(" ## EigenExa version (%d.%d) / (%s) / (%s)\n", v / 10000, (v / 100) % 100, date, vcode);
+}
+// eigen_loop_info_ (src/eigen_libs0.F:1744-1760)
+void eigen_loop_info(int istart, int iend, int *lstart, int *lend, int nnod, int inod)
+{
+    if (lstart) *lstart = eigen_loop_start(istart, nnod, inod);
+    if (lend) *lend = eigen_loop_end(iend, nnod, inod);
+}
+// eigen_convert_ID_xy2w / _w2xy (src/eigen_libs0.F:2316-2356), 1-based ids.  xy2w is restated as the
+// reference computes it (yinod*x_nnod + xinod, resp. xinod*y_nnod + yinod for order 'R'): it is NOT the
+// inverse of w2xy there either, and callers see exactly these values.
+int eigen_convert_id_xy2w(int xinod, int yinod)
+{
+    const Grid &g = ctx().g;
+    return g.order == 'R' ? xinod * g.py + yinod : yinod * g.px + xinod;
+}
+void eigen_convert_id_w2xy(int inod, int *xinod, int *yinod)
+{
+    const Grid &g = ctx().g;
+    int x, y;
+    if (g.order == 'R') { x = (inod - 1) / g.py + 1; y = (inod - 1) % g.py + 1; }
+    else { x = (inod - 1) % g.px + 1; y = (inod - 1) / g.px + 1; }
+    if (xinod) *xinod = x;
+    if (yinod) *yinod = y;
+}
+// eigen_get_comm (C/EigenExa.h:40, src/eigen_libs0.F:1655-1669).  There is no MPI in this build: the three
+// "communicators" are described by the same POD eigen_init takes -- rank / size of this process in the world,
+// in its x group (process column: ranks sharing y) and in its y group; rank = -1 before eigen_init.
+void eigen_get_comm(eigenexa_b200_comm_t *comm, eigenexa_b200_comm_t *x_comm, eigenexa_b200_comm_t *y_comm)
+{
+    const Context &c = ctx();
+    const Grid &g = c.g;
+    eigenexa_b200_comm_t w, x, y;
+    memset(&w, 0, sizeof w); memset(&x, 0, sizeof x); memset(&y, 0, sizeof y);
+    if (c.initialized) {
+        w.rank = g.inod; w.nranks = g.nnod; x.rank = g.x; x.nranks = g.px; y.rank = g.y; y.nranks = g.py;
+        w.device = x.device = y.device = c.device;
+    } else {
+        w.rank = x.rank = y.rank = -1; w.device = x.device = y.device = -1;
+    }
+    if (comm) *comm = w;
+    if (x_comm) *x_comm = x;
+    if (y_comm) *y_comm = y;
+}
+// Fortran face: integer handles in place of MPI_Fint (0 world, 1 x group, 2 y group; -1 before eigen_init)
+void eigen_libs0_eigen_get_comm_(int *comm, int *x_comm, int *y_comm)
+{
+    const bool on = ctx().initialized;
+    if (comm) *comm = on ? 0 : -1;
+    if (x_comm) *x_comm = on ? 1 : -1;
+    if (y_comm) *y_comm = on ? 2 : -1;
+}
+void eigen_libs0_eigen_show_version_(void) { eigen_show_version(); }
+// the Fortran shim returns a default INTEGER (C/eigen_exa_interfaces.F90:105-111): bytes are clamped to INT_MAX
+int eigen_libs0_eigen_memory_internal_(int *n, int *lda, int *ldz, int *m1, int *m0)
+{
+    int64_t b = eigen_memory_internal(*n, *lda, *ldz, m1 ? *m1 : 48, m0 ? *m0 : 128);
+    return b > 2147483647LL ? 2147483647 : (int)b;
+}
+int eigen_libs0_eigen_loop_start_(int *i, int *nnod, int *inod) { return eigen_loop_start(*i, *nnod, *inod); }
+int eigen_libs0_eigen_loop_end_(int *i, int *nnod, int *inod) { return eigen_loop_end(*i, *nnod, *inod); }
+void eigen_libs0_eigen_loop_info_(int *istart, int *iend, int *lstart, int *lend, int *nnod, int *inod)
+{
+    eigen_loop_info(*istart, *iend, lstart, lend, *nnod, *inod);
+}
+int eigen_libs0_eigen_translate_l2g_(int *i, int *nnod, int *inod) { return eigen_translate_l2g(*i, *nnod, *inod); }
+int eigen_libs0_eigen_translate_g2l_(int *i, int *nnod, int *inod) { return eigen_translate_g2l(*i, *nnod, *inod); }
+int eigen_libs0_eigen_owner_node_(int *i, int *nnod, int *inod) { return eigen_owner_node(*i, *nnod, *inod); }
+int eigen_libs0_eigen_owner_index_(int *i, int *nnod, int *inod) { return eigen_owner_index(*i, *nnod, *inod); }
+int eigen_libs0_eigen_convert_id_xy2w_(int *x, int *y) { return eigen_convert_id_xy2w(*x, *y); }
+void eigen_libs0_eigen_convert_id_w2xy_(int *inod, int *x, int *y) { eigen_convert_id_w2xy(*inod, x, y); }
+// BLACS glue is out of scope: there is no BLACS context in this build
+int eigen_blacs_eigen_get_blacs_context_(void) { return -1; }
+
 // ---- stage-level entry points ---------------------------------------------------------------
 int eigenexa_b200_trd(int n, double *a, int lda, double *d, double *e, int m_forward)
 {

@@ -88,6 +88,33 @@ void eigen_libs0_eigen_get_procs_(int *nnod, int *x_nnod, int *y_nnod);
 void eigen_libs0_eigen_get_id_(int *inod, int *x_inod, int *y_inod);
 void eigen_libs0_eigen_get_errinfo_(int *info);
 
+/* ---- the rest of the reference's C-visible surface (C/eigen_exa_interfaces.h:3-33, C/EigenExa.h:40) -- */
+void eigen_show_version(void);                                     /* eigen_libs0.F:207-236  */
+void eigen_loop_info(int istart, int iend, int *lstart, int *lend,
+                     int nnod, int inod);                          /* eigen_libs0.F:1744-1760 */
+int eigen_convert_id_xy2w(int xinod, int yinod);                   /* eigen_libs0.F:2316-2334 (values as the reference computes them) */
+void eigen_convert_id_w2xy(int inod, int *xinod, int *yinod);      /* eigen_libs0.F:2336-2356 */
+/* eigen_get_comm(comm, x_comm, y_comm) (C/EigenExa.h:40): no MPI here, so the three communicators are
+ * described by the POD eigen_init takes: rank/nranks of this process in the world, in its x group (ranks
+ * sharing y_inod) and in its y group; rank = -1 before eigen_init.  unique_id is left zero.            */
+void eigen_get_comm(eigenexa_b200_comm_t *comm, eigenexa_b200_comm_t *x_comm,
+                    eigenexa_b200_comm_t *y_comm);
+/* Fortran face of the same (integer handles in place of MPI_Fint: 0 world, 1 x, 2 y; -1 = not initialised) */
+void eigen_libs0_eigen_get_comm_(int *comm, int *x_comm, int *y_comm);
+void eigen_libs0_eigen_show_version_(void);
+int eigen_libs0_eigen_memory_internal_(int *n, int *lda, int *ldz, int *m1, int *m0); /* bytes, clamped to INT_MAX */
+int eigen_libs0_eigen_loop_start_(int *istart, int *nnod, int *inod);
+int eigen_libs0_eigen_loop_end_(int *iend, int *nnod, int *inod);
+void eigen_libs0_eigen_loop_info_(int *istart, int *iend, int *lstart, int *lend, int *nnod, int *inod);
+int eigen_libs0_eigen_translate_l2g_(int *ictr, int *nnod, int *inod);
+int eigen_libs0_eigen_translate_g2l_(int *ictr, int *nnod, int *inod);
+int eigen_libs0_eigen_owner_node_(int *ictr, int *nnod, int *inod);
+int eigen_libs0_eigen_owner_index_(int *ictr, int *nnod, int *inod);
+int eigen_libs0_eigen_convert_id_xy2w_(int *xinod, int *yinod);
+void eigen_libs0_eigen_convert_id_w2xy_(int *inod, int *xinod, int *yinod);
+int eigen_blacs_eigen_get_blacs_context_(void);   /* BLACS glue is out of scope: always -1 */
+/* not provided: eigen_h / eigen_libs_eigen_h_ (Hermitian solver, out of scope) */
+
 /* ---- stage-level entry points (the reference's public module procedures) ----------
  * eigen_trd(n,a,lda,d,e,m)                 src/eigen_trd.F:82
  * eigen_common_trbakwy(n,nvec,a,lda,z,ldz,e,m,iblk)  src/trbakwy4.F:77

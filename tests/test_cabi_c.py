@@ -1,0 +1,70 @@
+"""The drop-in boundary seen from C: a translation unit compiled with gcc against include/eigenexa_b200.h and
+linked to libeigenexa_b200.so (no Python in between), mirroring the reference's C/c_test.c; and the symbol
+list of the reference's own headers (C/eigen_exa_interfaces.h:3-33, C/EigenExa.h:12-46) checked against the
+built library."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIBDIR = os.path.join(ROOT, "eigenexa_b200", "lib")
+
+# C/eigen_exa_interfaces.h:3-33 (Fortran-style, by reference) -- eigen_libs_eigen_h_ is the Hermitian solver (out of scope)
+REF_FORTRAN_SYMBOLS = [
+    "eigen_libs_eigen_init_", "eigen_libs_eigen_free_", "eigen_blacs_eigen_get_blacs_context_",
+    "eigen_libs_eigen_sx_", "eigen_libs_eigen_s_", "eigen_libs0_eigen_get_version_",
+    "eigen_libs0_eigen_show_version_", "eigen_libs_eigen_get_matdims_", "eigen_libs0_eigen_memory_internal_",
+    "eigen_libs0_eigen_get_comm_", "eigen_libs0_eigen_get_procs_", "eigen_libs0_eigen_get_id_",
+    "eigen_libs0_eigen_loop_start_", "eigen_libs0_eigen_loop_end_", "eigen_libs0_eigen_loop_info_",
+    "eigen_libs0_eigen_translate_l2g_", "eigen_libs0_eigen_translate_g2l_", "eigen_libs0_eigen_owner_node_",
+    "eigen_libs0_eigen_owner_index_", "eigen_libs0_eigen_convert_id_xy2w_", "eigen_libs0_eigen_convert_id_w2xy_",
+    "eigen_libs0_eigen_get_errinfo_",
+]
+# C/EigenExa.h:12-46 -- eigen_h out of scope
+REF_C_SYMBOLS = ["eigen_init", "eigen_free", "eigen_s", "eigen_sx", "eigen_get_version", "eigen_get_procs",
+                 "eigen_get_id", "eigen_get_comm", "eigen_get_matdims"]
+
+
+def _compile(src, exe):
+    cmd = ["gcc", "-O1", "-Wall", "-Werror", "-std=c99", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c", src), "-o", exe, "-L", LIBDIR, "-leigenexa_b200",
+           f"-Wl,-rpath,{LIBDIR}", "-lm"]
+    subprocess.check_call(cmd)
+
+
+def test_reference_symbol_lists_are_exported():
+    L = ctypes.CDLL(os.path.join(LIBDIR, "libeigenexa_b200.so"))
+    missing = [s for s in REF_FORTRAN_SYMBOLS + REF_C_SYMBOLS if not hasattr(L, s)]
+    assert not missing, missing
+
+
+def test_symbol_lists_match_reference_headers_when_present():
+    """In the build container the reference is mounted: the hard-coded lists above must be its headers' lists."""
+    ref = "/root/reference/C"
+    if not os.path.isdir(ref):
+        pytest.skip("reference not mounted (GPU box)")
+    txt = open(os.path.join(ref, "eigen_exa_interfaces.h")).read()
+    names = set(re.findall(r"extern\s+\w+\s+(\w+_)\s*\(", txt)) - {"eigen_libs_eigen_h_"}
+    assert names == set(REF_FORTRAN_SYMBOLS)
+    txt = open(os.path.join(ref, "EigenExa.h")).read()
+    names = set(re.findall(r"^void\s+(\w+)\s*\(", txt, flags=re.M)) - {"eigen_h"}
+    assert names == set(REF_C_SYMBOLS)
+
+
+def test_c_translation_unit_host_calls(tmp_path):
+    exe = str(tmp_path / "cabi_host")
+    _compile("cabi_host.c", exe)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "CABI_HOST_OK" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_c_translation_unit_solves_like_c_test(tmp_path):
+    """C/c_test.c:19-32: eigen_s on [-2 1; 1 -2] -> (-3, -1), through eigen_s and eigen_libs_eigen_s_ (all by pointer)."""
+    exe = str(tmp_path / "cabi_gpu")
+    _compile("cabi_gpu.c", exe)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "CABI_GPU_OK" in r.stdout, r.stdout + r.stderr
