@@ -81,11 +81,15 @@ __global__ void monotone_fix_kernel(int n, double *w)
         if (w[i] < w[i - 1]) w[i] = w[i - 1];
 }
 
-// ---- penta-diagonal: inertia of T - x I from the banded L D L^T recurrence ---------------------
-//   l2 = a(i,i-2)/q(i-2) ; t = a(i,i-1) - a(i,i-2) l(i-1,i-2) ; l1 = t/q(i-1)
-//   q(i) = a(i,i) - x - l1 t - l2 a(i,i-2)
-// (eigen_bisect2 / sturm2_LDLT, src/bisect2.F:371-678, counts the negative pivots of the same
-// factorisation; its 2x2-pivot safeguard is replaced by the pivmin guard of the tridiagonal code.)
+// ---- penta-diagonal: inertia of T - x I from a banded block L D L^T -------------------------------
+// eigen_bisect2 / sturm2_LDLT (src/bisect2.F:393-678) counts the negative pivots of an L D L^T factorisation with a
+// "diagonal-neighbour" pivoting strategy, because the unpivoted band recurrence is not backward stable (a tiny
+// pivot makes the multipliers blow up and the next pivot absorbs the sub-diagonal entry).  Same safeguard here,
+// written as Bunch's rule for band matrices without interchanges: the reduced matrix keeps a 2x2 window
+//     [ p s ]     p = R(i,i), s = R(i,i+1), r = R(i+1,i+1)      (everything right / below is still original)
+//     [ s r ]
+// 1x1 pivot p when sigma |p| >= alpha s^2 (alpha = (sqrt5-1)/2, sigma = size of T - xI), otherwise the 2x2 block is
+// eliminated at once (its inertia: det < 0 -> one negative pivot, det > 0 -> two or none by the sign of p + r).
 __global__ void bisect2_prep_kernel(int n, const double *d, const double *e1, const double *e2, double *bounds)
 {
     __shared__ double s_lo[256], s_hi[256], s_em[256];
@@ -107,23 +111,44 @@ __global__ void bisect2_prep_kernel(int n, const double *d, const double *e1, co
         double x = (fabs(lo) + fabs(hi)) * eps + eps * em;
         bounds[0] = lo - x; bounds[1] = hi + x;
         bounds[2] = 2.2250738585072014e-308 * fmax(1.0, em * em);
+        bounds[3] = fmax((hi - lo) + em, 2.2250738585072014e-308);   // sigma: bound of |T - xI| entries for x in [lo, hi]
     }
 }
 
 __device__ __forceinline__ int sturm2_count(int n, const double *__restrict__ d, const double *__restrict__ e1,
-                                            const double *__restrict__ e2, double x, double pivmin)
+                                            const double *__restrict__ e2, double x, double pivmin, double sigma)
 {
-    int cnt = 0;
-    double q2 = 1.0, q1 = 1.0, lprev = 0.0;   // q(i-2), q(i-1), l(i-1,i-2)
-    for (int i = 0; i < n; i++) {
-        const double a2 = (i > 1) ? e2[i] : 0.0, a1 = (i > 0) ? e1[i] : 0.0;
-        const double l2 = a2 / q2;
-        const double t = a1 - a2 * lprev;
-        const double l1 = t / q1;
-        double q = d[i] - x - l1 * t - l2 * a2;
-        if (fabs(q) < pivmin) q = -pivmin;
-        cnt += (q < 0.0);
-        q2 = q1; q1 = q; lprev = l1;
+    const double alpha = 0.6180339887498949;
+    int cnt = 0, i = 0;
+    double p = d[0] - x;
+    double s = (n > 1) ? e1[1] : 0.0;
+    double r = (n > 1) ? d[1] - x : 0.0;
+    while (i < n) {
+        const double f = (i + 2 < n) ? e2[i + 2] : 0.0;      // R(i+2, i)
+        const double g = (i + 2 < n) ? e1[i + 2] : 0.0;      // R(i+2, i+1)
+        if (i == n - 1 || sigma * fabs(p) >= alpha * s * s) {
+            if (!(fabs(p) >= pivmin)) p = -pivmin;            // also catches a non-finite window
+            cnt += (p < 0.0);
+            const double sp = s / p, fp = f / p;
+            const double pn = r - s * sp;
+            const double sn = g - s * fp;
+            const double rn = (i + 2 < n) ? (d[i + 2] - x) - f * fp : 0.0;
+            p = pn; s = sn; r = rn;
+            i += 1;
+        } else {
+            double det = p * r - s * s;
+            if (!(fabs(det) >= pivmin)) det = -pivmin;
+            cnt += (det < 0.0) ? 1 : ((p + r < 0.0) ? 2 : 0);
+            const double h = (i + 3 < n) ? e2[i + 3] : 0.0;  // R(i+3, i+1)
+            const double upu = (r * f * f - 2.0 * s * f * g + p * g * g) / det;
+            const double upv = h * (p * g - s * f) / det;
+            const double vpv = p * h * h / det;
+            const double pn = (i + 2 < n) ? (d[i + 2] - x) - upu : 0.0;
+            const double sn = (i + 3 < n) ? e1[i + 3] - upv : 0.0;
+            const double rn = (i + 3 < n) ? (d[i + 3] - x) - vpv : 0.0;
+            p = pn; s = sn; r = rn;
+            i += 2;
+        }
     }
     return cnt;
 }
@@ -134,13 +159,13 @@ __global__ void bisect2_kernel(int n, const double *__restrict__ d, const double
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     double lb = bounds[0], ub = bounds[1];
-    const double pivmin = bounds[2];
+    const double pivmin = bounds[2], sigma = bounds[3];
     double x = lb;
     for (int it = 0; it < 2048; it++) {
         double t = x;
         x = 0.5 * (lb + ub);
         if (x == t || x <= lb || x >= ub) break;
-        int s = sturm2_count(n, d, e1, e2, x, pivmin);
+        int s = sturm2_count(n, d, e1, e2, x, pivmin, sigma);
         if (s <= k) lb = x; else ub = x;
     }
     w[k] = x;

@@ -39,30 +39,41 @@ Context &ctx()
     return c;
 }
 
-// Workspace comes from the device's stream-ordered memory pool on the library stream: a solve
-// allocates and frees tens of GB (padded copy of A, the D&C matrices); cudaMalloc/cudaFree of such
-// blocks cost hundreds of ms each and synchronise the device, the pool hands the same pages back to
-// the next stage / the next call.  eigen_free returns everything to the driver.
+// Workspace comes from a PRIVATE stream-ordered memory pool on the library stream: a solve allocates and
+// frees tens of GB (padded copy of A, the D&C matrices); cudaMalloc/cudaFree of such blocks cost hundreds
+// of ms each and synchronise the device, the pool hands the same pages back to the next stage / the next
+// call.  The pool belongs to the library (the device's default pool, which the host application or PyTorch
+// may use, is left alone); eigen_free destroys it, which returns every page to the driver.
+static cudaMemPool_t g_pool = nullptr;
 void *dev_alloc(size_t bytes)
 {
     void *p = nullptr;
     if (bytes == 0) bytes = 8;
-    EE_CUDA(cudaMallocAsync(&p, bytes, ctx().stream));
+    if (g_pool) EE_CUDA(cudaMallocFromPoolAsync(&p, bytes, g_pool, ctx().stream));
+    else EE_CUDA(cudaMallocAsync(&p, bytes, ctx().stream));
     return p;
 }
 void dev_free(void *p)
 {
     if (p) EE_CUDA(cudaFreeAsync(p, ctx().stream));
 }
-static void pool_configure(int device, bool release_all)
+static void pool_create(int device)
 {
-    cudaMemPool_t pool;
-    EE_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    if (release_all) { EE_CUDA(cudaMemPoolTrimTo(pool, 0)); return; }
-    // keep freed workspace mapped between stages and calls (N = 50000: 20 GB copies of A and Z, 3 x 20 GB in the
-    // D&C) -- the working set of the next call; eigen_free hands it back
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof props);
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    EE_CUDA(cudaMemPoolCreate(&g_pool, &props));
+    // keep freed workspace mapped between stages and calls (N = 50000: 20 GB copies of A and Z, 2 x 20 GB in the
+    // D&C) -- the working set of the next call
     unsigned long long keep = ~0ull;
-    EE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    EE_CUDA(cudaMemPoolSetAttribute(g_pool, cudaMemPoolAttrReleaseThreshold, &keep));
+}
+static void pool_destroy()
+{
+    if (g_pool) { cudaMemPoolDestroy(g_pool); g_pool = nullptr; }
 }
 
 // grid shape chosen by eigen_init (src/eigen_libs0.F:526-540)
@@ -165,10 +176,11 @@ static void eigen_s_impl(int n, int nvec, double *a, int lda, double *w, double 
     m_f = m_f < n ? m_f : n; if (m_f < 1) m_f = 1;
     int m_b = m_backward <= 0 ? 128 : m_backward;
     m_b = m_b < n ? m_b : n; if (m_b < 1) m_b = 1;
-    const int nv = nvec < 0 ? -nvec : nvec;
+    int nv = nvec < 0 ? -nvec : nvec;
+    if (nv > n) nv = n;                       // |nvec| smallest eigenpairs, at most n (z is sized with min(|nvec|, n))
     const Grid &g = c.g;
     const int nrl = cyc_count(n, g.px, g.x), ncl = cyc_count(n, g.py, g.y);
-    const int nvl = cyc_count(nv < n ? nv : n, g.py, g.y);
+    const int nvl = cyc_count(nv, g.py, g.y);
     if (lda < nrl || (mode != 'N' && ldz < nrl)) { set_error("eigen_s: lda/ldz smaller than the local row count"); return; }
 
     auto t_host0 = std::chrono::steady_clock::now();
@@ -196,6 +208,7 @@ static void eigen_s_impl(int n, int nvec, double *a, int lda, double *w, double 
     double *e2_d = penta ? (double *)dev_alloc((size_t)n * sizeof(double)) : nullptr;
     T.mark(1);
     double ret1 = 0, ret2 = 0, ret3 = 0;
+    bool a_copied_back = false;
     // ---- scaling (eigen_s.F:155-160) --------------------------------------------------------
     double sigma = scaling_dev(n, a_d, lda_d);
     bool done = false;
@@ -212,6 +225,16 @@ static void eigen_s_impl(int n, int nvec, double *a, int lda, double *w, double 
         else trd_dev(n, a_d, lda_d, (mode == 'N') ? d_d : w_d, e_d, m_f);
         ret1 = (double)n * n * n * 4.0 / 3.0;
         T.mark(2);
+        if (!dev_ptrs && nrl > 0 && ncl > 0) {
+            // a on exit holds the Householder reflectors like the reference's (src/eigen_trd_t7.F:208, SURVEY 8(b)
+            // "a is clobbered"): copied back on the side stream while the tridiagonal stage runs (no PCIe use there)
+            EE_CUDA(cudaEventRecord(c.ev_side, st));
+            EE_CUDA(cudaStreamWaitEvent(c.stream2, c.ev_side, 0));
+            if (lda == ldd) EE_CUDA(cudaMemcpyAsync(a, a_d, (size_t)ldd * ncl * sizeof(double), cudaMemcpyDeviceToHost, c.stream2));
+            else EE_CUDA(cudaMemcpy2DAsync(a, (size_t)lda * sizeof(double), a_d, (size_t)ldd * sizeof(double),
+                                           (size_t)nrl * sizeof(double), ncl, cudaMemcpyDeviceToHost, c.stream2));
+            a_copied_back = true;
+        }
         if (mode == 'N') {
             // eigen_bisect(d,e,w,n,0); NB the reference jumps to the exit without undoing
             // the scaling in this mode (eigen_s.F:219-234) -- kept.
@@ -247,6 +270,7 @@ static void eigen_s_impl(int n, int nvec, double *a, int lda, double *w, double 
     } else { T.mark(2); T.mark(3); T.mark(4); }
     T.mark(5);
     EE_CUDA(cudaStreamSynchronize(st));
+    if (a_copied_back) EE_CUDA(cudaStreamSynchronize(c.stream2));
     c.timings[0] = T.sec(0, 1); c.timings[1] = T.sec(1, 2); c.timings[2] = T.sec(2, 3);
     c.timings[3] = T.sec(3, 4); c.timings[4] = T.sec(4, 5);
     // ---- a(1:3,1) = flop count, seconds, comm seconds (-1: timers off) (eigen_s.F:284-295) ---
@@ -322,7 +346,8 @@ void eigen_init(const eigenexa_b200_comm_t *comm, const char *order)
     c.g = g;
     EE_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     EE_CUDA(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
-    pool_configure(c.device, false);
+    EE_CUDA(cudaEventCreateWithFlags(&c.ev_side, cudaEventDisableTiming));
+    pool_create(c.device);
     if (comm_init(comm ? comm->unique_id : nullptr, rank, nranks, g) != 0) return;
     c.initialized = true;
 }
@@ -335,7 +360,8 @@ void eigen_free(void)
     comm_finalize();
     for (cudaEvent_t e : c.ev_pool) cudaEventDestroy(e);
     c.ev_pool.clear();
-    pool_configure(c.device, true);
+    pool_destroy();
+    if (c.ev_side) { cudaEventDestroy(c.ev_side); c.ev_side = nullptr; }
     cudaStreamDestroy(c.stream); cudaStreamDestroy(c.stream2);
     c.stream = c.stream2 = nullptr;
     c.initialized = false;

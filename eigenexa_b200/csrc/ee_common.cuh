@@ -61,6 +61,7 @@ struct Context {
     int device = 0;
     cudaStream_t stream = nullptr;   // main stream: every kernel of the path
     cudaStream_t stream2 = nullptr;  // copies / side work
+    cudaEvent_t ev_side = nullptr;   // main stream -> side stream hand-over
     Comm *comm = nullptr;
     int errinfo = 0;
     int profiling = 0;  // 0 off; 1 async CUDA events around symv/syr2k launches; 2 sync per kernel class

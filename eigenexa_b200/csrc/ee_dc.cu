@@ -455,7 +455,10 @@ int dc_band_dev(int n, int nvec, const double *d_in, const double *e_in, const d
         if ((env && env[0] == '1') || repl_bytes > 100e9) rows_mode = true;
         if (env && env[0] == '0') rows_mode = false;
     }
-    const int RP = rows_mode ? P : 1, rw = rows_mode ? g.inod : 0;     // row partition: row gr on rank gr % RP
+    // row partition: row gr belongs to the row owner q = gr % RP, and rank (x, y) IS owner q = x + y px whatever
+    // the rank order of eigen_init ('C' or 'R'): the exchange below relies on jl % py = y'
+    const int RP = rows_mode ? P : 1, rw = rows_mode ? g.x + g.y * g.px : 0;
+    auto world_rank_of = [&](int x, int y) { return g.order == 'R' ? x * g.py + y : x + y * g.px; };
     auto lrows = [&](int gcount) { return cyc_count(gcount, RP, rw); };  // owned rows with global index < gcount
     const int nrow_loc = lrows(n);
     // (+4 rows of slack in the distributed form: the final exchange reuses Q / Q2 as receive / send buffers of
@@ -754,7 +757,7 @@ int dc_band_dev(int n, int nvec, const double *d_in, const double *e_in, const d
             comm_group_start();
             for (int y = 0; y < py; y++) {
                 if (y == g.y) continue;
-                const int peer = g.x + y * px;
+                const int peer = world_rank_of(g.x, y);
                 const size_t scount = (size_t)(soff[y + 1] - soff[y]), rcount = (size_t)(roff[y + 1] - roff[y]);
                 if (scount) comm_send(Q2 + soff[y], scount, peer, st);
                 if (rcount) comm_recv(Q + roff[y], rcount, peer, st);

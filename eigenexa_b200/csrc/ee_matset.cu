@@ -125,11 +125,153 @@ void mat_set_host(int n, double *a, int lda, int mtype, uint64_t seed, const Gri
     for (auto &t : th) t.join();
 }
 
+// ---- distributed form (benchmark/ev_test.f:81-164 runs on the grid: PDGEMM on block-cyclic copies) --------
+// Rank (x, y) holds A(x::px, y::py), Z(x::px, y::py); w is replicated.  Here BOTH triangles of the local part of
+// A must be filled (as mat_set_dev does): the mirror of a lower-triangle element lives on another rank.
+//   R_loc = sum over K chunks of  A(x rows, chunk) Z(chunk, y cols)  - Z_loc diag(w_y)
+//     A chunk: all-gather over the y group of KC/py local columns; Z chunk: all-gather over the x group of
+//     KC/px packed local rows, permuted to the K order of the gathered A chunk
+//   G_loc = sum over row chunks of  Z(rows, y cols)^T Z(rows, all cols)   (all-gather over the y group),
+//     summed over the x group; minus I
+namespace {
+// dst(r, c) = src(r, c0 + c) for c0 + c < ncols else 0     (nrows x cnt, ld = nrows)
+__global__ void pack_cols_kernel(const double *src, int lds, int nrows, int ncols, int c0, int cnt, double *dst)
+{
+    for (int c = blockIdx.y; c < cnt; c += gridDim.y)
+        for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x)
+            dst[(size_t)c * nrows + r] = (c0 + c < ncols) ? src[(size_t)(c0 + c) * lds + r] : 0.0;
+}
+// dst(r, c) = src(r0 + r, c) for r0 + r < nrows, c < ncols else 0     (cnt x ncols_pad, ld = cnt)
+__global__ void pack_rows2_kernel(const double *src, int lds, int nrows, int ncols, int r0, int cnt, int ncols_pad, double *dst)
+{
+    for (int c = blockIdx.y; c < ncols_pad; c += gridDim.y)
+        for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < cnt; r += gridDim.x * blockDim.x)
+            dst[(size_t)c * cnt + r] = (r0 + r < nrows && c < ncols) ? src[(size_t)c * lds + r0 + r] : 0.0;
+}
+// K order of the gathered A chunk: t = y' (KC/py) + c  <->  global k = k0 + c py + y'  <->  x' = kk % px, r = kk / px
+__global__ void permute_zchunk_kernel(const double *zg, int KC, int px, int py, int ncols, double *zch)
+{
+    const int kx = KC / px, ky = KC / py;
+    for (int j = blockIdx.y; j < ncols; j += gridDim.y)
+        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < KC; t += gridDim.x * blockDim.x) {
+            const int yp = t / ky, cc = t - yp * ky;
+            const int kk = cc * py + yp;
+            const int xp = kk % px, r = kk / px;
+            zch[(size_t)j * KC + t] = zg[((size_t)xp * ncols + j) * kx + r];
+        }
+}
+__global__ void sub_zw_cyc_kernel(int nrl, int nvl, double *r, int ldr, const double *z, int ldz, const double *w, int py, int y)
+{
+    for (int c = blockIdx.y; c < nvl; c += gridDim.y) {
+        const double wc = w[(size_t)c * py + y];
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nrl; j += gridDim.x * blockDim.x)
+            r[(size_t)c * ldr + j] -= wc * z[(size_t)c * ldz + j];
+    }
+}
+__global__ void sub_eye_off_kernel(int nv, double *g, int ldg, int col0)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < nv) g[(size_t)(col0 + c) * ldg + c] -= 1.0;
+}
+
+void ev_test_dist(int n, int nvec, const double *a, int lda, const double *w, const double *z, int ldz, double *out)
+{
+    Context &c = ctx();
+    const Grid &g = c.g;
+    cudaStream_t st = c.stream;
+    const double eps = 2.220446049250313e-16;
+    const int px = g.px, py = g.py;
+    const int nrl = cyc_count(n, px, g.x), ncl = cyc_count(n, py, g.y), nvl = cyc_count(nvec, py, g.y);
+    const int nvl_max = (nvec + py - 1) / py;
+    const int nrl1 = nrl > 0 ? nrl : 1;
+    int KC = 4096;                         // multiple of px and py (grids 1x2, 2x2, 2x4, ...)
+    while (KC % px || KC % py) KC += 64;
+    const int kx = KC / px, ky = KC / py;
+    double *scr = (double *)dev_alloc(64);
+    double sums[3] = {0, 0, 0};            // |A|^2, |R|^2, |G|^2 (local parts)
+    sums[0] = (nrl > 0 && ncl > 0) ? fro2(st, nrl, ncl, a, lda, scr) : 0.0;
+    // ---- R = A Z - Z W ---------------------------------------------------------------------------------
+    {
+        const int nvl1 = nvl > 0 ? nvl : 1;
+        double *R = (double *)dev_alloc((size_t)nrl1 * nvl1 * sizeof(double));
+        double *Ap = (double *)dev_alloc((size_t)nrl1 * ky * sizeof(double));
+        double *Ag = (double *)dev_alloc((size_t)nrl1 * KC * sizeof(double));
+        double *Zp = (double *)dev_alloc((size_t)kx * nvl1 * sizeof(double));
+        double *Zg = (double *)dev_alloc((size_t)KC * nvl1 * sizeof(double));
+        double *Zc = (double *)dev_alloc((size_t)KC * nvl1 * sizeof(double));
+        EE_CUDA(cudaMemsetAsync(R, 0, (size_t)nrl1 * nvl1 * sizeof(double), st));
+        for (int k0 = 0; k0 < n; k0 += KC) {
+            if (nrl > 0) {
+                dim3 grid(std::min(64, (nrl + 255) / 256), ky);
+                pack_cols_kernel<<<grid, 256, 0, st>>>(a, lda, nrl, ncl, k0 / py, ky, Ap);
+                EE_CHECK_LAUNCH();
+            }
+            comm_allgather(Ap, Ag, (size_t)nrl * ky, COMM_Y, st);
+            if (nvl > 0) {
+                dim3 grid((kx + 255) / 256, std::min(nvl, 32768));
+                pack_rows2_kernel<<<grid, 256, 0, st>>>(z, ldz, nrl, nvl, k0 / px, kx, nvl, Zp);
+                EE_CHECK_LAUNCH();
+            }
+            comm_allgather(Zp, Zg, (size_t)kx * nvl, COMM_X, st);
+            if (nrl > 0 && nvl > 0) {
+                dim3 grid((KC + 255) / 256, std::min(nvl, 32768));
+                permute_zchunk_kernel<<<grid, 256, 0, st>>>(Zg, KC, px, py, nvl, Zc);
+                EE_CHECK_LAUNCH();
+                dgemm(st, 'N', 'N', nrl, nvl, KC, 1.0, Ag, nrl, Zc, KC, 1.0, R, nrl);
+            }
+        }
+        if (nrl > 0 && nvl > 0) {
+            dim3 grid(std::min(64, (nrl + 255) / 256), std::min(nvl, 32768));
+            sub_zw_cyc_kernel<<<grid, 256, 0, st>>>(nrl, nvl, R, nrl, z, ldz, w, py, g.y);
+            EE_CHECK_LAUNCH();
+            sums[1] = fro2(st, nrl, nvl, R, nrl, scr);
+        }
+        dev_free(R); dev_free(Ap); dev_free(Ag); dev_free(Zp); dev_free(Zg); dev_free(Zc);
+    }
+    // ---- G = Z^T Z - I ---------------------------------------------------------------------------------
+    {
+        const int RC = 2048;
+        const int ncols_all = py * nvl_max;
+        const int nvl1 = nvl > 0 ? nvl : 1;
+        double *G = (double *)dev_alloc((size_t)nvl1 * ncols_all * sizeof(double));
+        double *Zr = (double *)dev_alloc((size_t)RC * nvl_max * sizeof(double));
+        double *Za = (double *)dev_alloc((size_t)RC * ncols_all * sizeof(double));
+        EE_CUDA(cudaMemsetAsync(G, 0, (size_t)nvl1 * ncols_all * sizeof(double), st));
+        const int nrl_max = (n + px - 1) / px;
+        for (int r0 = 0; r0 < nrl_max; r0 += RC) {
+            dim3 grid((RC + 255) / 256, std::min(nvl_max, 32768));
+            pack_rows2_kernel<<<grid, 256, 0, st>>>(z, ldz, nrl, nvl, r0, RC, nvl_max, Zr);
+            EE_CHECK_LAUNCH();
+            comm_allgather(Zr, Za, (size_t)RC * nvl_max, COMM_Y, st);
+            if (nvl > 0) dgemm(st, 'T', 'N', nvl, ncols_all, RC, 1.0, Zr, RC, Za, RC, 1.0, G, nvl);
+        }
+        comm_allreduce_sum(G, (size_t)nvl1 * ncols_all, COMM_X, st);
+        if (nvl > 0 && g.x == 0) {
+            sub_eye_off_kernel<<<(nvl + 255) / 256, 256, 0, st>>>(nvl, G, nvl, g.y * nvl_max);
+            EE_CHECK_LAUNCH();
+            sums[2] = fro2(st, nvl, ncols_all, G, nvl, scr);
+        }
+        dev_free(G); dev_free(Zr); dev_free(Za);
+    }
+    double *dsum = (double *)dev_alloc(4 * sizeof(double));
+    EE_CUDA(cudaMemcpyAsync(dsum, sums, 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    comm_allreduce_sum(dsum, 3, COMM_WORLD, st);
+    EE_CUDA(cudaMemcpyAsync(sums, dsum, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EE_CUDA(cudaStreamSynchronize(st));
+    const double anorm = sqrt(sums[0]);
+    out[0] = sqrt(sums[1]) / ((double)n * eps * anorm);
+    out[1] = sqrt(sums[2]) / ((double)n * eps);
+    out[2] = anorm;
+    dev_free(dsum); dev_free(scr);
+}
+}  // namespace
+
 // single-rank check (the reference redistributes to block-cyclic and calls PDGEMM; one GPU
 // holds the N = 50000 problem, so the check runs where the data already is)
 void ev_test_dev(int n, int nvec, const double *a, int lda, const double *w, const double *z, int ldz, double *out)
 {
     Context &c = ctx();
+    if (c.g.nnod > 1) { ev_test_dist(n, nvec, a, lda, w, z, ldz, out); return; }
     cudaStream_t st = c.stream;
     const double eps = 2.220446049250313e-16;
     const int ldf = (n + 15) & ~15;

@@ -258,6 +258,12 @@ def w_set(n: int, mtype: int, seed: int = 0) -> np.ndarray | None:
         s = np.random.default_rng(seed).random(n)
         s = np.maximum(s, 1e-300)
         return np.sqrt(-2 * np.log(s)) * np.sin(2 * np.pi * s)
+    if mtype == 10:
+        # spectrum read from benchmark/W.dat (mat_set.f:714-729); its first 2000 values are committed as a fixture
+        head = np.load(os.path.join(os.path.dirname(_HERE), "tests", "golden", "w_dat_head.npy"))
+        if n > head.shape[0]:
+            raise ValueError("mat_set type 10: only the first 2000 values of W.dat are committed")
+        return head[:n].copy()
     return None
 
 
@@ -273,7 +279,7 @@ def helmert(n: int) -> np.ndarray:
 
 
 def mat_set(n: int, mtype: int, seed: int = 1) -> np.ndarray:
-    """Global test matrix (Fortran order).  Types 0-3 via the C generator, 4-9 Helmert."""
+    """Global test matrix (Fortran order).  Types 0-3 via the C generator, 4-10 Helmert."""
     if mtype in (0, 1, 2, 3):
         a = np.zeros((n, n), order="F")
         lib().ora_mat_set_local(mtype, n, _dp(a), n, 1, 1, 1, 1, seed)

@@ -26,10 +26,10 @@ int main(void)
     int nnod = 0, xn = 0, yn = 0, inod = 0, xi = 0, yi = 0;
     eigen_get_procs(&nnod, &xn, &yn);
     eigen_get_id(&inod, &xi, &yi);
-    if (nnod != 1) { printf("eigen_init failed: %s\n", eigenexa_b200_last_error()); return 2; }
-    CHECK(xn == 1 && yn == 1 && inod == 1 && xi == 1 && yi == 1);
     eigenexa_b200_comm_t cw, cx, cy;
     eigen_get_comm(&cw, &cx, &cy);
+    if (cw.rank < 0 || nnod != 1) { printf("eigen_init failed: %s\n", eigenexa_b200_last_error()); return 2; }
+    CHECK(xn == 1 && yn == 1 && inod == 1 && xi == 1 && yi == 1);
     CHECK(cw.rank == 0 && cw.nranks == 1 && cx.nranks == 1 && cy.nranks == 1);
 
     int n = 2, nv = 2, lda = 2, ldz = 2, mf = 1, mb = 1;

@@ -75,6 +75,29 @@ def test_bisect2(ee, n):
     assert np.abs(w - np.linalg.eigvalsh(B)).max() <= 10 * n * O.EPS * max(np.linalg.norm(B), 1.0)
 
 
+@pytest.mark.parametrize("n,kind", [(200, "chains"), (301, "chains"), (257, "integer"), (400, "biharmonic"), (300, "tridiag"),
+                                    (64, "zero")])
+def test_bisect2_exact_pivot_hits(ee, n, kind):
+    """Band matrices whose leading principal minors are singular at (or next to) eigenvalues of the whole matrix: the
+    unpivoted band L D L^T recurrence breaks down there; the 2x2-pivot safeguard (src/bisect2.F:393-678) must not."""
+    rng = np.random.default_rng(n)
+    if kind == "chains":        # e1 = 0: two interleaved tridiagonal chains, every eigenvalue (nearly) double
+        d, e1, e2 = np.zeros(n), np.zeros(n), np.ones(n)
+    elif kind == "integer":
+        d, e1, e2 = (rng.integers(-2, 3, n).astype(float) for _ in range(3))
+    elif kind == "biharmonic":
+        d, e1, e2 = np.full(n, 6.0), np.full(n, -4.0), np.ones(n)
+    elif kind == "tridiag":
+        d, e1, e2 = np.zeros(n), np.ones(n), np.zeros(n)
+    else:
+        d, e1, e2 = np.zeros(n), np.zeros(n), np.zeros(n)
+    e1[0] = 0.0; e2[:2] = 0.0
+    w = ee.eigen_bisect2(n, d, e1, e2)
+    B = O.band_from(d, e1, e2)
+    assert np.all(np.isfinite(w)) and np.all(np.diff(w) >= 0)
+    assert np.abs(w - np.linalg.eigvalsh(B)).max() <= 10 * n * O.EPS * max(np.linalg.norm(B), 1.0)
+
+
 @pytest.mark.parametrize("n,mtype,mb,nvec", [(5, 2, 128, 5), (50, 2, 8, 50), (300, 0, 128, 300), (513, 2, 128, 513),
                                              (1000, 2, 128, 250)])
 def test_trbak_nb2_matches_oracle(ee, n, mtype, mb, nvec):

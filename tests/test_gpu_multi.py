@@ -1,4 +1,6 @@
-"""GPU, >= 2 devices: eigen_s on a 2D cyclic grid (NCCL) vs the oracle.  Skipped on one GPU."""
+"""GPU, >= 2 devices: eigen_s / eigen_sx on a 2D cyclic grid (NCCL + NVLink peer memory) vs LAPACK and the ev_test gates.
+Skipped on one GPU.  Variants: rank order 'R', the NCCL fallback of the per-column all-reduce (EIGENEXA_B200_NO_PEER=1),
+the row-distributed and the replicated form of the divide & conquer (EIGENEXA_B200_DC_ROWS=1 / 0)."""
 import json
 import os
 import subprocess
@@ -15,24 +17,42 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("nproc,n,mtype,mode,solver", [(2, 600, 2, "A", "s"), (2, 257, 0, "A", "s"), (2, 500, 2, "N", "s"),
-                                                       (2, 1300, 2, "A", "s"), (4, 700, 2, "A", "s"), (4, 1500, 0, "A", "s"),
-                                                       (8, 900, 2, "A", "s"),
-                                                       # penta-diagonal driver on the same grids
-                                                       (2, 601, 2, "A", "sx"), (2, 1300, 0, "A", "sx"), (2, 500, 2, "N", "sx"),
-                                                       (4, 1500, 2, "A", "sx")])
-# (eigen_sx on the 2x4 grid: not yet run on hardware in round 1 -- its grid-dependent code, symv_strip / pvec partial sums /
-#  staircase GEMM, is the code eigen_s exercises on 2x4; add the case once an 8-GPU slot has confirmed it)
-def test_eigen_s_multi_rank(nproc, n, mtype, mode, solver):
+CASES = [
+    # nproc, n, mtype, mode, solver, order, env
+    (2, 600, 2, "A", "s", "C", {}), (2, 257, 0, "A", "s", "C", {}), (2, 500, 2, "N", "s", "C", {}),
+    (2, 1300, 2, "A", "s", "C", {}), (4, 700, 2, "A", "s", "C", {}), (4, 1500, 0, "A", "s", "C", {}),
+    (8, 900, 2, "A", "s", "C", {}),
+    # penta-diagonal driver on the same grids
+    (2, 601, 2, "A", "sx", "C", {}), (2, 1300, 0, "A", "sx", "C", {}), (2, 500, 2, "N", "sx", "C", {}),
+    (4, 1500, 2, "A", "sx", "C", {}), (8, 1100, 2, "A", "sx", "C", {}),
+    # both D&C distributions, forced
+    (2, 1300, 2, "A", "s", "C", {"EIGENEXA_B200_DC_ROWS": "1"}), (2, 1300, 2, "A", "s", "C", {"EIGENEXA_B200_DC_ROWS": "0"}),
+    (4, 1500, 2, "A", "s", "C", {"EIGENEXA_B200_DC_ROWS": "1"}), (4, 1500, 2, "A", "sx", "C", {"EIGENEXA_B200_DC_ROWS": "1"}),
+    (8, 1700, 2, "A", "s", "C", {"EIGENEXA_B200_DC_ROWS": "1"}), (8, 1700, 2, "A", "sx", "C", {"EIGENEXA_B200_DC_ROWS": "1"}),
+    (8, 1700, 2, "A", "s", "C", {"EIGENEXA_B200_DC_ROWS": "0"}),
+    # row-major rank order (eigen_init(comm, 'R'), src/eigen_libs0.F:553-556)
+    (2, 600, 2, "A", "s", "R", {}), (4, 700, 2, "A", "s", "R", {"EIGENEXA_B200_DC_ROWS": "1"}),
+    (8, 900, 2, "A", "s", "R", {"EIGENEXA_B200_DC_ROWS": "1"}), (8, 900, 2, "A", "sx", "R", {}),
+    # NCCL all-reduce per column instead of the peer-memory one
+    (2, 600, 2, "A", "s", "C", {"EIGENEXA_B200_NO_PEER": "1"}), (2, 601, 2, "A", "sx", "C", {"EIGENEXA_B200_NO_PEER": "1"}),
+    (4, 700, 2, "A", "s", "C", {"EIGENEXA_B200_NO_PEER": "1"}),
+]
+
+
+@pytest.mark.parametrize("nproc,n,mtype,mode,solver,order,env", CASES)
+def test_eigen_s_multi_rank(nproc, n, mtype, mode, solver, order, env):
     if _ngpu() < nproc:
         pytest.skip(f"needs {nproc} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr",
            "127.0.0.1", "--master-port", str(29500 + nproc), os.path.join(ROOT, "tools", "run_multi.py"), str(n),
-           str(mtype), mode, "check", solver]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+           str(mtype), mode, "check", solver, order]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env={**os.environ, **env})
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     out = json.loads(line)
     assert out["w_err_over_tol"] <= 1.0
     if mode != "N":
         assert out["residual"] <= 10 and out["orth"] <= 10
+        # the distributed on-device ev_test (benchmark/ev_test.f:81-164 on the grid) sees the same numbers
+        assert abs(out["residual_dev"] - out["residual"]) <= 0.05 * out["residual"] + 1e-3
+        assert abs(out["orth_dev"] - out["orth"]) <= 0.05 * out["orth"] + 1e-3
