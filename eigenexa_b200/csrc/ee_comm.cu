@@ -196,6 +196,13 @@ bool comm_peer_setup(size_t slot_doubles, PeerView *view)
 }
 
 unsigned long long comm_peer_next_epoch() { return ++ctx().comm->epoch; }
+unsigned long long comm_peer_reserve_epochs(int n)
+{
+    Comm *m = ctx().comm;
+    const unsigned long long first = m->epoch + 1;
+    m->epoch += (unsigned long long)(n > 0 ? n : 0);
+    return first;
+}
 
 void comm_finalize()
 {

@@ -41,5 +41,7 @@ struct PeerView {
 // returns true when the peer ring is usable with at least slot_doubles per slot
 bool comm_peer_setup(size_t slot_doubles, PeerView *view);
 unsigned long long comm_peer_next_epoch();
+// reserves n consecutive epochs (one per column of a persistent panel launch); returns the first
+unsigned long long comm_peer_reserve_epochs(int n);
 
 }  // namespace ee

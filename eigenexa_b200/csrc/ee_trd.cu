@@ -58,7 +58,19 @@ struct TrdP {
     double *d_out, *e_out;
     int has_next;                       // vvec: build next column
     int first;                          // vvec: panel prologue only (no v to form)
+    int piv; double upiv;               // persistent kernel: u(piv) is upiv (not yet visible in ucur), piv = -1: none
 };
+
+// Loads of vectors that other CTAs write during the same launch (persistent panel kernel) must bypass the
+// non-coherent L1 / read-only path: COH = true -> ld.global.cg.  The multi-launch kernels keep ld.global.nc.
+template <bool COH>
+__device__ __forceinline__ double ldv(const double *p) { return COH ? __ldcg(p) : __ldg(p); }
+template <bool COH>
+__device__ __forceinline__ double ldu(const TrdP &P, const double *u, long long g)
+{
+    if (COH && g == P.piv) return P.upiv;
+    return ldv<COH>(u + g);
+}
 
 // --- staircase geometry shared by writer (symv) and reader (pvec) ------------------------
 // number of local columns with global index < L
@@ -116,7 +128,7 @@ struct SymvIO {
     double *pcol[NV];        // col partials  [tile row][col]
 };
 
-template <int NV>
+template <int NV, bool COH = false>
 __device__ __forceinline__ void symv_strip(const TrdP &P, const SymvIO<NV> &io, int br, int sc, int nclL, double *smem)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -129,7 +141,7 @@ __device__ __forceinline__ void symv_strip(const TrdP &P, const SymvIO<NV> &io, 
         long long g = (long long)rloc[q] * P.px + P.x;
 #pragma unroll
         for (int v = 0; v < NV; v++) {
-            ux[v][q] = (g < P.L) ? __ldg(io.u[v] + g) : 0.0;
+            ux[v][q] = (g < P.L) ? ldu<COH>(P, io.u[v], g) : 0.0;
             acc_row[v][q] = 0.0;
         }
     }
@@ -170,7 +182,7 @@ __device__ __forceinline__ void symv_strip(const TrdP &P, const SymvIO<NV> &io, 
 #pragma unroll
             for (int c = 0; c < 8; c++) {
                 const long long g = (long long)(cw + c) * P.py + P.y;
-                const double uy = (g < P.L) ? __ldg(io.u[v] + g) : 0.0;
+                const double uy = (g < P.L) ? ldu<COH>(P, io.u[v], g) : 0.0;
                 acc_row[v][0] = fma(v0[c].x, uy, acc_row[v][0]);
                 acc_row[v][1] = fma(v0[c].y, uy, acc_row[v][1]);
                 acc_row[v][2] = fma(v1[c].x, uy, acc_row[v][2]);
@@ -229,7 +241,7 @@ __device__ __forceinline__ void symv_strip(const TrdP &P, const SymvIO<NV> &io, 
 
 // chunk of the panel dot products  s_l = V_l^T u, t_l = U_l^T u  (finished slots first..first+nd-1)
 // for NV vectors; results st[v*2*MAXM + (0..nd-1 | nd..2nd-1)]
-template <int NV>
+template <int NV, bool COH = false>
 __device__ void dots_chunk(const TrdP &P, const double *const *uvec, int first_slot, int ch)
 {
     const int nd = P.ndone;
@@ -244,9 +256,9 @@ __device__ void dots_chunk(const TrdP &P, const double *const *uvec, int first_s
 #pragma unroll
         for (int v = 0; v < NV; v++) s[v] = 0.0;
         for (int j = j0 + lane; j < j1; j += 32) {
-            const double cj = __ldg(col + j);
+            const double cj = ldv<COH>(col + j);
 #pragma unroll
-            for (int v = 0; v < NV; v++) s[v] = fma(cj, __ldg(uvec[v] + j), s[v]);
+            for (int v = 0; v < NV; v++) s[v] = fma(cj, ldu<COH>(P, uvec[v], j), s[v]);
         }
 #pragma unroll
         for (int v = 0; v < NV; v++) {
@@ -254,6 +266,7 @@ __device__ void dots_chunk(const TrdP &P, const double *const *uvec, int first_s
             if (lane == 0) P.dots_part[((size_t)ch * NV + v) * 2 * MAXM + c] = t;
         }
     }
+    if (COH) return;   // persistent kernel: every CTA sums the NCH partials itself after the grid barrier
     // last chunk CTA reduces the partials in fixed order
     __shared__ unsigned int s_last;
     __threadfence();
@@ -530,6 +543,393 @@ __global__ void __launch_bounds__(VR * VS) vvec_kernel(TrdP P)
             P.tickets[2] = 0u;
         }
     }
+}
+
+// =========================================================================================
+// Persistent panel kernel: ALL column steps of one panel in ONE cooperative launch.
+//
+// The three launches per column (symv -> pvec -> vvec) cost ~15-20 us of launch gaps and kernel tails per column
+// on one GPU and ~45 us on a grid (plus the 11 us launch floor of a small SYMV): with 50000 dependent columns that is
+// the strong-scaling limiter.  Here the CTAs stay resident (2 per SM) and the kernel boundaries become grid
+// barriers on a monotonic counter; the Householder scalars are reduced redundantly, in the same fixed order, by
+// every CTA, so no CTA ever waits for a "last block" to publish them.
+//   per column:  [S] SYMV tiles + panel dot products, handed out by a ticket counter (dynamic balance)
+//                --- grid barrier ---
+//                [P] p = sum of tile partials (+ diag) ; on a grid: partial -> every rank's peer slot,
+//                    --- grid barrier, epoch flag to every rank, wait for the P flags ---  p = sum of the P slots
+//                    p -= U s + V t ; partial u^T p per CTA
+//                --- grid barrier ---  alpha
+//                [V] v = (p - alpha u)/beta -> panel ; next column from the panel copy (left-looking) ; norm partial
+//                --- grid barrier ---  g, u_L, beta of the next column (u_L is substituted on the fly in [S], every
+//                    other phase sees it through memory)
+// Every vector another CTA writes during the launch is read with ld.global.cg (L1 is not coherent); only the
+// matrix itself, which is constant for the whole panel, keeps the streaming loads.
+// Every spin has a watchdog (__trap): a protocol error aborts the launch instead of hanging the GPU.
+// =========================================================================================
+struct PanelCtl {
+    unsigned long long *bar;     // grid barrier counter, zeroed by the host before the launch
+    unsigned long long *work;    // work ticket counter, zeroed by the host before the launch
+    double *partA, *partB;       // [gridDim.x] per-CTA partial sums (u^T p / next-column norm)
+    double *tacc;                // [4] accumulated nanoseconds: 0 SYMV phase, 1 p phase, 2 v phase (CTA 0), or nullptr
+    int k_stop;                  // last slot to process (2 for the first panel, else 0)
+    unsigned long long epoch0;   // peer epoch of the first column of this launch (multi-rank)
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// all CTAs of the (co-resident) grid; target = number of arrivals that completes this barrier
+__device__ __forceinline__ void grid_barrier(unsigned long long *bar, unsigned long long target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1ull);
+        unsigned int spins = 0;
+        while (ld_acquire_gpu(bar) < target) {
+            if (++spins > (1u << 27)) __trap();      // seconds: a CTA never arrived
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <int NT>
+__device__ __forceinline__ int block_max_int(int v, int *sm)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = sm[0];
+#pragma unroll
+    for (int i = 1; i < NT / 32; i++) r = max(r, sm[i]);
+    return r;       // valid in every thread
+}
+// sum of per-CTA partials, identical in every thread of every CTA (fixed order)
+template <int NT>
+__device__ __forceinline__ double grid_sum(const double *part, int nparts, double *sm)
+{
+    double s = 0.0;
+    for (int q = threadIdx.x; q < nparts; q += NT) s += __ldcg(part + q);
+    s = warp_sum(s);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    double r = 0.0;
+#pragma unroll
+    for (int i = 0; i < NT / 32; i++) r += sm[i];
+    return r;
+}
+
+template <bool MULTI>
+__global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, PanelCtl C)
+{
+    __shared__ double smem[8 * TR];          // SYMV row-sum exchange; reused by the vector phases
+    __shared__ double s_st[2 * MAXM];
+    __shared__ int s_nbr[1024];
+    __shared__ double s_ur[MAXM], s_vr[MAXM];
+    __shared__ double s_red[8];
+    __shared__ int s_redi[8];
+    __shared__ long long s_item;
+    double(*s_acc)[VR] = reinterpret_cast<double(*)[VR]>(smem);   // [VS][VR]
+    const int G = gridDim.x, bid = blockIdx.x, tid = threadIdx.x;
+    const int m0 = P.m0, i_base = P.i_base;
+    unsigned long long nbar = 0;             // barriers passed so far
+    unsigned long long work_base = 0;        // tickets consumed by the finished columns
+    const bool timing = (C.tacc != nullptr) && bid == 0 && tid == 0;
+    unsigned long long t_mark = 0;
+    double *ucur = P.ucur, *unext = P.unext;
+    double sc_g = 0.0, sc_un = 0.0, sc_beta = 1.0;   // Householder scalars of the current column (replicated per CTA)
+    const int r = tid & 31, sl = tid >> 5;
+
+    // ---- next column (slot kn, diagonal row top) from the panel copy; returns its scalars ------------------------
+    // first: panel prologue (no finished pair to apply, no v to form)
+    auto v_phase = [&](int k, int L, bool first, bool has_next, double alpha, double beta, double *u_c, double *u_n,
+                       double &g_out, double &un_out, double &beta_out) {
+        const int c = L - 1;
+        const int lo = first ? k + 1 : k;
+        const int nl = m0 - lo;
+        if (has_next) {
+            for (int l = tid; l < nl; l += 256) {
+                const int slot = lo + l;
+                double ur, vr;
+                if (!first && slot == k) {
+                    ur = __ldcg(u_c + c);
+                    vr = (__ldcg(P.pbuf + c) - alpha * ur) / beta;
+                } else {
+                    ur = __ldcg(P.U + (size_t)slot * P.npad + c);
+                    vr = __ldcg(P.V + (size_t)slot * P.npad + c);
+                }
+                s_ur[l] = ur; s_vr[l] = vr;
+            }
+        }
+        __syncthreads();
+        const int kn = first ? k : k - 1;
+        const int top = first ? L : c;
+        const int nrows = first ? L + 1 : L;
+        double nrm_cta = 0.0;
+        for (int rb = bid; rb * VR < nrows; rb += G) {
+            const int g = rb * VR + r;
+            double acc = 0.0;
+            if (g < nrows) {
+                double ug = 0.0, vg = 0.0;
+                if (!first) {
+                    ug = __ldcg(u_c + g);
+                    vg = (__ldcg(P.pbuf + g) - alpha * ug) / beta;
+                    if (sl == 0) {
+                        P.U[(size_t)k * P.npad + g] = ug;
+                        P.V[(size_t)k * P.npad + g] = vg;
+                    }
+                }
+                if (has_next && g <= top) {
+                    if (sl == 0) acc = __ldcg(P.W + (size_t)kn * P.npad + g);
+                    for (int l = sl; l < nl; l += VS) {
+                        const int slot = lo + l;
+                        double uj, vj;
+                        if (!first && slot == k) { uj = ug; vj = vg; }
+                        else { uj = __ldcg(P.U + (size_t)slot * P.npad + g); vj = __ldcg(P.V + (size_t)slot * P.npad + g); }
+                        acc = fma(-uj, s_vr[l], acc);
+                        acc = fma(-vj, s_ur[l], acc);
+                    }
+                }
+            }
+            if (has_next) {
+                __syncthreads();
+                s_acc[sl][r] = acc;
+                __syncthreads();
+                if (sl == 0) {
+                    double a = 0.0;
+#pragma unroll
+                    for (int q = 0; q < VS; q++) a += s_acc[q][r];
+                    double nrm = 0.0;
+                    if (g <= top) {
+                        u_n[g] = a;
+                        if (g < top) nrm = a * a;
+                    }
+                    nrm = warp_sum(nrm);
+                    nrm_cta += nrm;      // lane-uniform after warp_sum
+                }
+            }
+        }
+        if (!has_next) return;
+        if (tid == 0) C.partB[bid] = nrm_cta;
+        grid_barrier(C.bar, (++nbar) * (unsigned long long)G);
+        const double anorm2 = grid_sum<256>(C.partB, G, s_red);
+        const double a_n = __ldcg(u_n + top - 1);
+        double g_n, u_piv, bt;
+        if (anorm2 != 0.0) {
+            const double nr = sqrt(anorm2);
+            g_n = -copysign(nr, a_n);
+            u_piv = a_n - g_n;
+            bt = -u_piv * g_n;
+        } else { g_n = 0.0; u_piv = 0.0; bt = 1.0; }
+        if (bid == 0 && tid == 0) {
+            const double dia = __ldcg(u_n + top);
+            u_n[top - 1] = u_piv;        // visible to the phases behind the next grid barrier; [S] substitutes it
+            P.e_out[top] = g_n;
+            P.d_out[top] = dia;
+        }
+        g_out = g_n; un_out = u_piv; beta_out = bt;
+    };
+
+    // ---- panel prologue: first column of the panel is the raw panel copy ---------------------------------------
+    {
+        const int k = m0 - 1, L = i_base + m0 - 1;
+        v_phase(k, L, true, true, 0.0, 1.0, ucur, ucur, sc_g, sc_un, sc_beta);
+    }
+
+    for (int k = m0 - 1; k >= C.k_stop; k--) {
+        const int L = i_base + k;
+        const int ndone = m0 - 1 - k;
+        const bool has_next = (k - 1 >= C.k_stop);
+        TrdP Q = P;
+        Q.k = k; Q.L = L; Q.ndone = ndone; Q.ucur = ucur; Q.unext = unext;
+        Q.piv = L - 1; Q.upiv = sc_un;
+        const int nclL = cyc_count(L, P.py, P.y);
+        const int sw = (L > 12288) ? 4 : (L > 6144) ? 2 : 1;
+        Q.sw = sw;
+        const int nsc = (nclL + sw * TC - 1) / (sw * TC);
+        const int gx = (nsc + 1) / 2;
+        // rows of the biggest strip + rows of the smallest (fold_triangle), max over the CTA columns
+        int gy = 0;
+        for (int bx = tid; bx < gx; bx += 256) {
+            const int s1 = nsc - 1 - bx, s2 = bx;
+            int rr = strip_rows(Q, s1, nclL) + (s2 != s1 ? strip_rows(Q, s2, nclL) : 0);
+            gy = max(gy, rr);
+        }
+        gy = block_max_int<256>(gy, s_redi);
+        for (int s_ = tid; s_ < nsc && s_ < 1024; s_ += 256) s_nbr[s_] = strip_rows(Q, s_, nclL);
+        const long long ntile = (long long)gx * gy;
+        const long long nitems = ntile + (ndone > 0 ? NCH : 0);
+        if (timing) t_mark = globaltimer_ns();
+        // ================= [S] SYMV tiles + panel dot products =================================================
+        {
+            SymvIO<1> io;
+            io.u[0] = ucur; io.prow[0] = P.Prow; io.pcol[0] = P.Pcol;
+            const double *uv[1] = {ucur};
+            long long next = 0;
+            if (tid == 0) next = (long long)(atomicAdd(C.work, 1ull) - work_base);
+            for (;;) {
+                if (tid == 0) s_item = next;
+                __syncthreads();
+                const long long item = s_item;
+                if (item >= nitems) break;
+                if (tid == 0) next = (long long)(atomicAdd(C.work, 1ull) - work_base);   // in flight during the strip
+                if (item < ntile) {
+                    int sc, br;
+                    if (fold_triangle(Q, (int)item, gx, nclL, sc, br)) symv_strip<1, true>(Q, io, br, sc, nclL, smem);
+                } else {
+                    dots_chunk<1, true>(Q, uv, k + 1, (int)(item - ntile));
+                }
+                __syncthreads();
+            }
+            work_base += (unsigned long long)nitems + (unsigned long long)G;   // every CTA draws exactly one ticket too many
+        }
+        grid_barrier(C.bar, (++nbar) * (unsigned long long)G);
+        if (timing) { const unsigned long long t = globaltimer_ns(); C.tacc[0] += (double)(t - t_mark); t_mark = t; }
+        // ================= [P] p, alpha ============================================================================
+        for (int cc = tid; cc < 2 * ndone; cc += 256) {
+            double t = 0.0;
+            for (int q = 0; q < NCH; q++) t += __ldcg(P.dots_part + (size_t)q * 2 * MAXM + cc);
+            s_st[cc] = t;
+        }
+        __syncthreads();
+        const int par = MULTI ? (int)((C.epoch0 + (unsigned long long)(m0 - 1 - k)) & 1ull) : 0;
+        const unsigned long long epoch = C.epoch0 + (unsigned long long)(m0 - 1 - k);
+        double up_cta = 0.0;
+        // partial sums of the tile partials of row block rb (all 256 threads) -> value in threads sl == 0
+        auto partial_p = [&](int g) -> double {
+            double acc = 0.0;
+            if (g < L) {
+                const bool rown = (g % P.px) == P.x, coln = (g % P.py) == P.y;
+                if (rown) {
+                    const int jl = g / P.px, brr = jl / TR;
+                    for (int s_ = nsc - 1 - sl; s_ >= 0 && s_nbr[s_] > brr; s_ -= VS) acc += __ldcg(P.Prow + (size_t)s_ * P.ldprow + jl);
+                }
+                if (coln) {
+                    const int il = g / P.py;
+                    const int nb = ntile_rows(Q, il / TC, nclL);
+                    for (int b = sl; b < nb; b += VS) acc += __ldcg(P.Pcol + (size_t)b * P.ldpcol + il);
+                    if (rown && sl == 0) acc = fma(P.A[(size_t)il * P.lda + g / P.px], ldu<true>(Q, ucur, g), acc);
+                }
+            }
+            return acc;
+        };
+        auto corrections = [&](int g, double acc) -> double {
+            if (g < L) {
+                for (int l = sl; l < ndone; l += VS) {
+                    const size_t off = (size_t)(k + 1 + l) * P.npad + g;
+                    acc = fma(-__ldcg(P.U + off), s_st[l], acc);
+                    acc = fma(-__ldcg(P.V + off), s_st[ndone + l], acc);
+                }
+            }
+            return acc;
+        };
+        if (!MULTI) {
+            for (int rb = bid; rb * VR < L; rb += G) {
+                const int g = rb * VR + r;
+                double acc = partial_p(g);
+                acc = corrections(g, acc);
+                __syncthreads();
+                s_acc[sl][r] = acc;
+                __syncthreads();
+                if (sl == 0) {
+                    double p = 0.0;
+#pragma unroll
+                    for (int q = 0; q < VS; q++) p += s_acc[q][r];
+                    double up = 0.0;
+                    if (g < L) { P.pbuf[g] = p; up = ldu<true>(Q, ucur, g) * p; }
+                    up_cta += warp_sum(up);
+                }
+            }
+        } else {
+            // partial -> slot[par][my rank] of EVERY rank (NVLink stores)
+            for (int rb = bid; rb * VR < L; rb += G) {
+                const int g = rb * VR + r;
+                const double acc = partial_p(g);
+                __syncthreads();
+                s_acc[sl][r] = acc;
+                __syncthreads();
+                if (sl == 0 && g < L) {
+                    double p = 0.0;
+#pragma unroll
+                    for (int q = 0; q < VS; q++) p += s_acc[q][r];
+                    const size_t off = ((size_t)par * pv.P + pv.r) * pv.slot_doubles + g;
+                    for (int q = 0; q < pv.P; q++) pv.slots[q][off] = p;
+                }
+            }
+            __threadfence_system();
+            grid_barrier(C.bar, (++nbar) * (unsigned long long)G);
+            if (bid == 0 && tid == 0) {
+                __threadfence_system();
+                for (int q = 0; q < pv.P; q++) st_release_sys(pv.flags[q] + (size_t)par * pv.P + pv.r, epoch);
+            }
+            if (tid == 0) {
+                const unsigned long long *fl = pv.flags[pv.r] + (size_t)par * pv.P;
+                for (int q = 0; q < pv.P; q++) {
+                    unsigned int spins = 0;
+                    while (ld_acquire_sys(fl + q) < epoch) {
+                        if (++spins > (1u << 27)) { *pv.err = 1; __trap(); }   // a peer never arrived
+                    }
+                }
+                __threadfence_system();
+            }
+            __syncthreads();
+            for (int rb = bid; rb * VR < L; rb += G) {
+                const int g = rb * VR + r;
+                double acc = 0.0;
+                if (sl == 0 && g < L) {
+                    const double *base = pv.slots[pv.r] + (size_t)par * pv.P * pv.slot_doubles + g;
+                    for (int q = 0; q < pv.P; q++) acc += __ldcg(base + (size_t)q * pv.slot_doubles);
+                }
+                acc = corrections(g, acc);
+                __syncthreads();
+                s_acc[sl][r] = acc;
+                __syncthreads();
+                if (sl == 0) {
+                    double p = 0.0;
+#pragma unroll
+                    for (int q = 0; q < VS; q++) p += s_acc[q][r];
+                    double up = 0.0;
+                    if (g < L) { P.pbuf[g] = p; up = ldu<true>(Q, ucur, g) * p; }
+                    up_cta += warp_sum(up);
+                }
+            }
+        }
+        if (tid == 0) C.partA[bid] = up_cta;
+        grid_barrier(C.bar, (++nbar) * (unsigned long long)G);
+        const double alpha = grid_sum<256>(C.partA, G, s_red) / (2.0 * sc_beta);   // u^T p / (2 beta)  (trd_t6_3.F:255-262)
+        if (timing) { const unsigned long long t = globaltimer_ns(); C.tacc[1] += (double)(t - t_mark); t_mark = t; }
+        // ================= [V] v, next column, its scalars =========================================================
+        double g_n = 0.0, u_n = 0.0, b_n = 1.0;
+        v_phase(k, L, false, has_next, alpha, sc_beta, ucur, unext, g_n, u_n, b_n);
+        if (timing) { const unsigned long long t = globaltimer_ns(); C.tacc[2] += (double)(t - t_mark); t_mark = t; }
+        sc_g = g_n; sc_un = u_n; sc_beta = b_n;
+        double *tmp = ucur; ucur = unext; unext = tmp;
+    }
+    (void)sc_g;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1130,11 +1530,13 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
     size_t oDots = take((size_t)NCH * 2 * MAXM), oSt = take(2 * MAXM), oPart = take(2 * (size_t)maxvb);
     size_t oScal = take(32), oTick = take(32);
     size_t oUVx = take((size_t)lda * 2 * mmax), oVUy = take((size_t)nclp * 2 * mmax);
+    size_t oCtl = take(32), oPartAB = take(2 * 2048);
     double *ws = (double *)dev_alloc(wsz * sizeof(double));
     EE_CUDA(cudaMemsetAsync(ws, 0, wsz * sizeof(double), st));
 
     TrdP P;
     memset(&P, 0, sizeof P);
+    P.piv = -1;
     P.A = A; P.lda = lda; P.px = g.px; P.py = g.py; P.x = g.x; P.y = g.y;
     P.n = n; P.npad = npad;
     P.U = ws + oU; P.V = ws + oV; P.W = ws + oW;
@@ -1149,6 +1551,28 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
     memset(&pv, 0, sizeof pv);
     // (two vectors per slot, as eigen_prd needs: a later eigen_sx of the same size then reuses the ring as it is)
     const bool use_peer = multi && comm_peer_setup((size_t)2 * npad, &pv);
+
+    // ---- persistent panel kernel (one cooperative launch per panel) unless switched off / debugging ----------
+    bool persist = (!multi || use_peer) && c.debug_maxcols == 0 && c.profiling < 2;
+    {
+        const char *e = getenv("EIGENEXA_B200_TRD_PERSIST");
+        if (e && e[0] == '0') persist = false;
+    }
+    int pgrid = 0;
+    PanelCtl ctl;
+    memset(&ctl, 0, sizeof ctl);
+    if (persist) {
+        int per_sm = 0;
+        if (multi) EE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trd_panel_kernel<true>, 256, 0));
+        else EE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trd_panel_kernel<false>, 256, 0));
+        pgrid = per_sm * c.sm_count;
+        if (pgrid > 2048) pgrid = 2048;
+        if (pgrid < 1) persist = false;
+        ctl.bar = reinterpret_cast<unsigned long long *>(ws + oCtl);
+        ctl.work = ctl.bar + 1;
+        ctl.tacc = c.profiling ? ws + oCtl + 4 : nullptr;
+        ctl.partA = ws + oPartAB; ctl.partB = ctl.partA + 2048;
+    }
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float t_symv = 0.f, t_syr2k = 0.f, t_pvec = 0.f, t_vvec = 0.f;
@@ -1205,8 +1629,22 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
             EE_CHECK_LAUNCH();
             if (multi) comm_allreduce_sum(P.W, (size_t)npad * m0, COMM_WORLD, st);
         }
+        if (persist) {
+            // every column step of the panel in one cooperative launch
+            TrdP Q = P;
+            EE_CUDA(cudaMemsetAsync(ctl.bar, 0, 2 * sizeof(unsigned long long), st));
+            PanelCtl C = ctl;
+            C.k_stop = k_stop;
+            C.epoch0 = multi ? comm_peer_reserve_epochs(m0 - k_stop) : 0ull;
+            void *args[] = {(void *)&Q, (void *)&pv, (void *)&C};
+            prof_begin(1);
+            if (multi) EE_CUDA(cudaLaunchCooperativeKernel((void *)trd_panel_kernel<true>, dim3(pgrid), dim3(256), args, 0, st));
+            else EE_CUDA(cudaLaunchCooperativeKernel((void *)trd_panel_kernel<false>, dim3(pgrid), dim3(256), args, 0, st));
+            EE_CHECK_LAUNCH();
+            prof_end(t_symv, 1);
+        }
         // panel prologue: first column of the panel (slot m0-1) is the raw panel copy
-        {
+        if (!persist) {
             TrdP Q = P;
             Q.k = m0 - 1; Q.L = i_base + m0 - 1; Q.first = 1; Q.has_next = 1; Q.ndone = 0;
             Q.unext = P.ucur;  // write straight into ucur
@@ -1214,7 +1652,7 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
             vvec_kernel<<<nb, VR * VS, 0, st>>>(Q);
             EE_CHECK_LAUNCH();
         }
-        for (int k = m0 - 1; k >= k_stop; k--) {
+        for (int k = m0 - 1; k >= k_stop && !persist; k--) {
             const int i = i_base + k, L = i;
             if (c.debug_maxcols > 0 && (n - 1 - i) >= c.debug_maxcols) { col_end = 0; break; }
             TrdP Q = P;
@@ -1316,6 +1754,8 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
     if (nrl > 0 && ncl > 0)
         EE_CUDA(cudaMemcpy2DAsync(a_user, (size_t)lda_user * sizeof(double), A, (size_t)lda * sizeof(double),
                                   (size_t)nrl * sizeof(double), ncl, cudaMemcpyDeviceToDevice, st));
+    double tacc_h[4] = {0, 0, 0, 0};
+    if (persist && ctl.tacc) EE_CUDA(cudaMemcpyAsync(tacc_h, ctl.tacc, sizeof tacc_h, cudaMemcpyDeviceToHost, st));
     EE_CUDA(cudaStreamSynchronize(st));
     if (use_peer) {
         int herr = 0;
@@ -1339,6 +1779,9 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
     if (c.profiling) {
         c.timings[5] = t_symv * 1e-3; c.timings[6] = t_syr2k * 1e-3;
         c.timings[7] = t_pvec * 1e-3; c.timings[8] = t_vvec * 1e-3;
+        // persistent kernel: timings[5] is the event time of the panel kernels; the in-kernel split (globaltimer of
+        // CTA 0 around the phases of every column) goes to [15] SYMV phase, [16] p phase, [31] v phase
+        c.timings[15] = tacc_h[0] * 1e-9; c.timings[16] = tacc_h[1] * 1e-9; c.timings[31] = tacc_h[2] * 1e-9;
         c.timings[9] = tw1 - tw0; c.timings[10] = tw2 - tw1; c.timings[11] = tw3 - tw2; c.timings[12] = tw4 - tw3;
         cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     }
