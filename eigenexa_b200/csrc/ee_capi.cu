@@ -208,7 +208,7 @@ static void eigen_s_impl(int n, int nvec, double *a, int lda, double *w, double 
     double *e2_d = penta ? (double *)dev_alloc((size_t)n * sizeof(double)) : nullptr;
     T.mark(1);
     double ret1 = 0, ret2 = 0, ret3 = 0;
-    bool a_copied_back = false;
+    bool a_copied_back = false, z_streamed = false;
     // ---- scaling (eigen_s.F:155-160) --------------------------------------------------------
     double sigma = scaling_dev(n, a_d, lda_d);
     bool done = false;
@@ -253,6 +253,8 @@ static void eigen_s_impl(int n, int nvec, double *a, int lda, double *w, double 
             if (mode == 'X') { if (penta) bisect2_dev(n, d_d, e_d, e2_d, w_d); else bisect_dev(n, d_d, e_d, w_d); }
             T.mark(3);
             // ---- back-transformation (eigen_s.F:245-248) ------------------------------------
+            // host arrays: Z goes to the caller chunk by chunk on the side stream, behind the GEMMs of the next chunk
+            if (!dev_ptrs && nrl > 0 && nvl > 0) { trbak_set_host_output(z, ldz); z_streamed = true; }
             trbak_dev(n, nv, a_d, lda_d, z_d, ldz_d, penta ? e2_d : e_d, m_b, penta ? 2 : 1);   // nb = MBAND (eigen_sx.F:245)
             ret3 = 2.0 * (double)nv * (double)n * (double)n;
             // ---- undo the scaling (eigen_s.F:261-264) ---------------------------------------
@@ -260,17 +262,12 @@ static void eigen_s_impl(int n, int nvec, double *a, int lda, double *w, double 
                 scale_vec_dev(w_d, n, 1.0 / sigma, st);
             }
             T.mark(4);
-            if (!dev_ptrs && nrl > 0 && nvl > 0) {
-                if (ldz == ldz_d) EE_CUDA(cudaMemcpyAsync(z, z_d, (size_t)ldz_d * nvl * sizeof(double), cudaMemcpyDeviceToHost, st));
-                else EE_CUDA(cudaMemcpy2DAsync(z, (size_t)ldz * sizeof(double), z_d, (size_t)ldz_d * sizeof(double),
-                                               (size_t)nrl * sizeof(double), nvl, cudaMemcpyDeviceToHost, st));
-            }
         }
         if (!dev_ptrs) EE_CUDA(cudaMemcpyAsync(w, w_d, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     } else { T.mark(2); T.mark(3); T.mark(4); }
     T.mark(5);
     EE_CUDA(cudaStreamSynchronize(st));
-    if (a_copied_back) EE_CUDA(cudaStreamSynchronize(c.stream2));
+    if (a_copied_back || z_streamed) EE_CUDA(cudaStreamSynchronize(c.stream2));
     c.timings[0] = T.sec(0, 1); c.timings[1] = T.sec(1, 2); c.timings[2] = T.sec(2, 3);
     c.timings[3] = T.sec(3, 4); c.timings[4] = T.sec(4, 5);
     // ---- a(1:3,1) = flop count, seconds, comm seconds (-1: timers off) (eigen_s.F:284-295) ---

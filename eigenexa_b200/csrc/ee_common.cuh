@@ -86,6 +86,9 @@ double scaling_dev(int n, double *a, int lda);
 void trd_dev(int n, double *a, int lda, double *d_out, double *e_out, int m_forward);
 // eigen_common_trbakwy with z distributed 2D cyclic (ldz x nvl)
 void trbak_dev(int n, int nvec, const double *a, int lda, double *z, int ldz, const double *e, int m_backward, int iblk = 1);
+// the next trbak_dev call also delivers Z to this host array (ld ldz_host), chunk by chunk on the side stream;
+// the caller synchronises stream2 before it reads z_host
+void trbak_set_host_output(double *z_host, int ldz_host);
 // eigen_prd (penta-diagonal reduction): e1(i) = T(i-1,i), e2(i) = T(i-2,i)
 void prd_dev(int n, double *a, int lda, double *d_out, double *e1_out, double *e2_out, int m_forward);
 // tridiagonal divide and conquer; z (ldz x nvl) receives the local cyclic part
