@@ -323,20 +323,32 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    symv_s = float(stage[5])
+    # eigen_trd runs every column step of a panel inside ONE persistent kernel (trd_panel_kernel): stage[5] is the
+    # CUDA-event time around those launches, stage[15] the SYMV phase alone (in-kernel %globaltimer of CTA 0 around
+    # the phase of every column).  Without the persistent kernel (eigen_prd, fallbacks) stage[5] is the event time
+    # around every symv launch.
+    kern_s = float(stage[5])
+    persist = float(stage[15]) > 0.0
+    symv_s = float(stage[15]) if persist else kern_s
     bytes_rank = symv_bytes(n) / world
-    n_symv = max(n - 2, 1)
+    n_cols = max(n - 2, 1)
     if args.solver == "sx":
         bytes_rank *= 0.5      # one pass over the staircase per column PAIR (2/3 n^3 B)
-        n_symv = max((n - 2) // 2, 1)
-    achieved = bytes_rank / symv_s / 1e9 if symv_s > 0 else None
+        n_cols = max((n - 2) // 2, 1)
+    n_launch = n_cols
+    if persist:
+        n_launch, ce = 0, n
+        while ce > 2:
+            ce = ((ce - 1) // 48) * 48
+            n_launch += 1
+    achieved = bytes_rank / kern_s / 1e9 if kern_s > 0 else None
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "symv_ncu_traffic.json")))
-        # ncu --set full measured dram bytes / algorithmic bytes of one symv launch at L ~ N = 50000; the average launch
-        # of this run is smaller by the same factor on both sides
+        # ncu --set full measured dram bytes / algorithmic bytes of one launch; the average launch
+        # of this run is scaled by the same factor on both sides
         traffic_ratio = float(tj["traffic_over_algorithmic"])
-        traffic = traffic_ratio * bytes_rank / n_symv if args.solver == "s" else None
+        traffic = traffic_ratio * bytes_rank / n_launch if args.solver == "s" else None
     except Exception:
         pass
     fp64_peak = 35.4
@@ -344,23 +356,32 @@ def main():
         fp64_peak = float(json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))["cublas_dgemm_tflops"])
     except Exception:
         pass
-    roofline = {"kernel": "symv2_kernel" if args.solver == "sx" else "symv_kernel", "bound": "hbm", "achieved": achieved,
+    kname = ("trd_panel_kernel (persistent: SYMV over the upper triangle + vector phases of all columns of a panel)"
+             if persist else ("symv2_kernel" if args.solver == "sx" else "symv_kernel"))
+    roofline = {"kernel": kname, "bound": "hbm", "achieved": achieved,
                 "peak": hbm_peak, "unit": "GB/s",
                 "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic,
-                "traffic_source": "profiles/symv_ncu_traffic.json: dram bytes / algorithmic bytes of one symv launch at N = 50000 "
+                "traffic_source": "profiles/symv_ncu_traffic.json: dram bytes / algorithmic bytes of one launch "
                                   "(ncu --set full), scaled to this run's average launch", "peak_source": peak_src,
-                "launches_per_step": n_symv, "avg_launch_ms": symv_s / n_symv * 1e3,
-                "algorithmic_bytes_per_launch_avg": bytes_rank / n_symv,
+                "launches_per_step": n_launch, "avg_launch_ms": kern_s / n_launch * 1e3,
+                "algorithmic_bytes_per_launch_avg": bytes_rank / n_launch,
+                "algorithmic_bytes": "8 B x strict upper triangle of the trailing matrix, once per column (4/3 n^3 B per solve)",
                 "timing": "CUDA events on the library stream around every launch of the timed steps (this rank)"}
+    if persist:
+        roofline["symv_phase"] = {"seconds": symv_s, "achieved": bytes_rank / symv_s / 1e9,
+                                  "frac": bytes_rank / symv_s / 1e9 / hbm_peak,
+                                  "timing": "in-kernel %globaltimer of CTA 0 around the SYMV phase of every column "
+                                            "(phase start to the grid barrier that ends it)"}
     trd_s = float(stage[1])
-    ncols = max(n - 2, 1)
     stages = {"h2d_s": float(stage[0]), "trd_s": trd_s, "dc_s": float(stage[2]), "trbak_s": float(stage[3]),
               "symv_s": symv_s, "syr2k_s": float(stage[6]),
               "trd_other_s": trd_s - symv_s - float(stage[6]),
-              "trd_other_us_per_column": (trd_s - symv_s - float(stage[6])) / ncols * 1e6,
+              "trd_other_us_per_column": (trd_s - symv_s - float(stage[6])) / max(n - 2, 1) * 1e6,
               "syr2k_tflops": (2.0 / 3.0 * n ** 3 / world) / float(stage[6]) / 1e12 if stage[6] > 0 else None,
               "trbak_tflops": (2.0 * nvec * float(n) ** 2 / world) / float(stage[3]) / 1e12 if stage[3] > 0 else None,
               "fp64_tensor_peak_tflops": fp64_peak, "fp64_peak_source": "cuBLAS DGEMM 8192^3 measured on this pool"}
+    if persist:
+        stages.update({"panel_kernel_s": kern_s, "p_phase_s": float(stage[16]), "v_phase_s": float(stage[31])})
 
     def make_line(e2e, cpu, check, partial):
         line = {

@@ -22,10 +22,9 @@
 // Memory / multi-GPU layout.  The k x k secular eigenvector matrix is never stored: it is generated in
 // column blocks (<= 2 GB) that go straight into the merge GEMMs, so the work space is two n x n matrices.
 // Two distributions of the eigenvector matrix Q over P ranks:
-//   * replicated (default for P > 1 while 2 n^2 doubles fit comfortably): merges >= 1024 are split by
+//   * replicated (EIGENEXA_B200_DC_ROWS=0, only while 4 n^2 doubles fit): merges >= 1024 are split by
 //     column slices over the ranks and all-gathered;
-//   * ROW distributed (P = 1 trivially; P > 1 when the replicated form would not fit, or with
-//     EIGENEXA_B200_DC_ROWS=1): rank w owns the rows g = w (mod P).  Every step of the algorithm acts on
+//   * ROW distributed (the default; P = 1 trivially): row owner q = x + y px owns the rows g = q (mod P).  Every step of the algorithm acts on
 //     rows independently (rotations, column gathers, Q_new(rows,:) = Q_old(rows,:) V) except the four rows
 //     that form z (one small all-reduce per rank-one update); the O(n^2) secular work is replicated, no
 //     eigenvector data moves until the end, where the ranks that share a grid row exchange column sets to
@@ -448,12 +447,14 @@ int dc_band_dev(int n, int nvec, const double *d_in, const double *e_in, const d
 
     // ---- distribution of the eigenvector matrix -------------------------------------------------------
     const int P = g.nnod;
-    bool rows_mode = (P == 1);
+    // Row-distributed is the default on a grid: the merge GEMMs (all but a few % of the D&C time at N = 50000) are
+    // divided by P at every level and no eigenvector data moves until the final exchange; the replicated form
+    // (EIGENEXA_B200_DC_ROWS=0) all-gathers every merged block and needs 4 n^2 doubles per rank.
+    bool rows_mode = true;
     if (P > 1) {
         const char *env = getenv("EIGENEXA_B200_DC_ROWS");
         const double repl_bytes = 4.2 * (double)n * (double)n * sizeof(double);   // Q, Q2, slice + gather buffers
-        if ((env && env[0] == '1') || repl_bytes > 100e9) rows_mode = true;
-        if (env && env[0] == '0') rows_mode = false;
+        if (env && env[0] == '0' && repl_bytes <= 100e9) rows_mode = false;
     }
     // row partition: row gr belongs to the row owner q = gr % RP, and rank (x, y) IS owner q = x + y px whatever
     // the rank order of eigen_init ('C' or 'R'): the exchange below relies on jl % py = y'

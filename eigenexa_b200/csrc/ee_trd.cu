@@ -1997,6 +1997,7 @@ void prd_dev(int n, double *a_user, int lda_user, double *d_out, double *e1_out,
         };
         drain(pool_symv, t_symv, true); drain(pool_syr2k, t_syr2k, false);
         c.timings[5] = t_symv * 1e-3; c.timings[6] = t_syr2k * 1e-3;
+        c.timings[15] = c.timings[16] = c.timings[31] = 0.0;   // (no persistent kernel on this path)
     }
     dev_free(ws);
     dev_free(A);
