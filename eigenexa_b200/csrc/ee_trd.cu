@@ -128,20 +128,34 @@ struct SymvIO {
     double *pcol[NV];        // col partials  [tile row][col]
 };
 
+// COH (persistent kernel, NV = 1): the entries of u this strip needs -- SW*TC columns, TR rows -- are staged in
+// shared memory (su) with coalesced ld.global.cg loads up front: a coherent load inside the column loop would
+// be an L2 round trip per column on the critical path.
 template <int NV, bool COH = false>
-__device__ __forceinline__ void symv_strip(const TrdP &P, const SymvIO<NV> &io, int br, int sc, int nclL, double *smem)
+__device__ __forceinline__ void symv_strip(const TrdP &P, const SymvIO<NV> &io, int br, int sc, int nclL, double *smem,
+                                           double *su = nullptr)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r0 = br * TR;
     // this thread's 4 rows
     int rloc[4] = {r0 + 2 * lane, r0 + 2 * lane + 1, r0 + 64 + 2 * lane, r0 + 64 + 2 * lane + 1};
     double ux[NV][4], acc_row[NV][4];
+    if (COH) {
+        for (int idx = threadIdx.x; idx < SW * TC + TR; idx += blockDim.x) {
+            long long g;
+            if (idx < SW * TC) g = (long long)(sc * P.sw * TC + idx) * P.py + P.y;    // column idx of the strip
+            else g = (long long)(r0 + idx - SW * TC) * P.px + P.x;                     // row of the tile row
+            su[idx] = (g < P.L) ? ldu<true>(P, io.u[0], g) : 0.0;
+        }
+        __syncthreads();
+    }
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         long long g = (long long)rloc[q] * P.px + P.x;
 #pragma unroll
         for (int v = 0; v < NV; v++) {
-            ux[v][q] = (g < P.L) ? ldu<COH>(P, io.u[v], g) : 0.0;
+            if (COH) ux[v][q] = su[SW * TC + rloc[q] - r0];
+            else ux[v][q] = (g < P.L) ? ldu<COH>(P, io.u[v], g) : 0.0;
             acc_row[v][q] = 0.0;
         }
     }
@@ -182,7 +196,7 @@ __device__ __forceinline__ void symv_strip(const TrdP &P, const SymvIO<NV> &io, 
 #pragma unroll
             for (int c = 0; c < 8; c++) {
                 const long long g = (long long)(cw + c) * P.py + P.y;
-                const double uy = (g < P.L) ? ldu<COH>(P, io.u[v], g) : 0.0;
+                const double uy = COH ? su[st * TC + 8 * warp + c] : ((g < P.L) ? ldu<COH>(P, io.u[v], g) : 0.0);
                 acc_row[v][0] = fma(v0[c].x, uy, acc_row[v][0]);
                 acc_row[v][1] = fma(v0[c].y, uy, acc_row[v][1]);
                 acc_row[v][2] = fma(v1[c].x, uy, acc_row[v][2]);
@@ -571,6 +585,7 @@ struct PanelCtl {
     unsigned long long *work;    // work ticket counter, zeroed by the host before the launch
     double *partA, *partB;       // [gridDim.x] per-CTA partial sums (u^T p / next-column norm)
     double *tacc;                // [4] accumulated nanoseconds: 0 SYMV phase, 1 p phase, 2 v phase (CTA 0), or nullptr
+    double *pivraw;              // [2] raw pivot / diagonal element of the next column (written before the barrier)
     int k_stop;                  // last slot to process (2 for the first panel, else 0)
     unsigned long long epoch0;   // peer epoch of the first column of this launch (multi-rank)
 };
@@ -650,6 +665,7 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
     __shared__ double s_st[2 * MAXM];
     __shared__ int s_nbr[1024];
     __shared__ double s_ur[MAXM], s_vr[MAXM];
+    __shared__ double s_u[SW * TC + TR];     // entries of u of the strip in flight
     __shared__ double s_red[8];
     __shared__ int s_redi[8];
     __shared__ long long s_item;
@@ -727,6 +743,8 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
                     if (g <= top) {
                         u_n[g] = a;
                         if (g < top) nrm = a * a;
+                        if (g == top - 1) C.pivraw[0] = a;     // raw pivot element: every CTA reads it after the barrier
+                        if (g == top) C.pivraw[1] = a;         // diagonal element
                     }
                     nrm = warp_sum(nrm);
                     nrm_cta += nrm;      // lane-uniform after warp_sum
@@ -737,7 +755,8 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
         if (tid == 0) C.partB[bid] = nrm_cta;
         grid_barrier(C.bar, (++nbar) * (unsigned long long)G);
         const double anorm2 = grid_sum<256>(C.partB, G, s_red);
-        const double a_n = __ldcg(u_n + top - 1);
+        // (not from u_n[top-1]: CTA 0 overwrites that entry with u_piv below while other CTAs may still be here)
+        const double a_n = __ldcg(C.pivraw);
         double g_n, u_piv, bt;
         if (anorm2 != 0.0) {
             const double nr = sqrt(anorm2);
@@ -746,7 +765,7 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
             bt = -u_piv * g_n;
         } else { g_n = 0.0; u_piv = 0.0; bt = 1.0; }
         if (bid == 0 && tid == 0) {
-            const double dia = __ldcg(u_n + top);
+            const double dia = __ldcg(C.pivraw + 1);
             u_n[top - 1] = u_piv;        // visible to the phases behind the next grid barrier; [S] substitutes it
             P.e_out[top] = g_n;
             P.d_out[top] = dia;
@@ -799,7 +818,7 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
                 if (tid == 0) next = (long long)(atomicAdd(C.work, 1ull) - work_base);   // in flight during the strip
                 if (item < ntile) {
                     int sc, br;
-                    if (fold_triangle(Q, (int)item, gx, nclL, sc, br)) symv_strip<1, true>(Q, io, br, sc, nclL, smem);
+                    if (fold_triangle(Q, (int)item, gx, nclL, sc, br)) symv_strip<1, true>(Q, io, br, sc, nclL, smem, s_u);
                 } else {
                     dots_chunk<1, true>(Q, uv, k + 1, (int)(item - ntile));
                 }
@@ -826,11 +845,20 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
                 const bool rown = (g % P.px) == P.x, coln = (g % P.py) == P.y;
                 if (rown) {
                     const int jl = g / P.px, brr = jl / TR;
-                    for (int s_ = nsc - 1 - sl; s_ >= 0 && s_nbr[s_] > brr; s_ -= VS) acc += __ldcg(P.Prow + (size_t)s_ * P.ldprow + jl);
+                    // strips that reach this tile row: s_nbr is non-decreasing in s, so they are s >= s_lo
+                    // (known trip count: the loads of the loop can be batched)
+                    int s_lo = 0, s_hi = nsc;
+                    while (s_lo < s_hi) {
+                        const int mid = (s_lo + s_hi) >> 1;
+                        if (s_nbr[mid] > brr) s_hi = mid; else s_lo = mid + 1;
+                    }
+#pragma unroll 4
+                    for (int s_ = nsc - 1 - sl; s_ >= s_lo; s_ -= VS) acc += __ldcg(P.Prow + (size_t)s_ * P.ldprow + jl);
                 }
                 if (coln) {
                     const int il = g / P.py;
                     const int nb = ntile_rows(Q, il / TC, nclL);
+#pragma unroll 4
                     for (int b = sl; b < nb; b += VS) acc += __ldcg(P.Pcol + (size_t)b * P.ldpcol + il);
                     if (rown && sl == 0) acc = fma(P.A[(size_t)il * P.lda + g / P.px], ldu<true>(Q, ucur, g), acc);
                 }
@@ -1571,6 +1599,7 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
         ctl.bar = reinterpret_cast<unsigned long long *>(ws + oCtl);
         ctl.work = ctl.bar + 1;
         ctl.tacc = c.profiling ? ws + oCtl + 4 : nullptr;
+        ctl.pivraw = ws + oCtl + 8;
         ctl.partA = ws + oPartAB; ctl.partB = ctl.partA + 2048;
     }
 
