@@ -140,22 +140,28 @@ __device__ __forceinline__ void symv_strip(const TrdP &P, const SymvIO<NV> &io, 
     // this thread's 4 rows
     int rloc[4] = {r0 + 2 * lane, r0 + 2 * lane + 1, r0 + 64 + 2 * lane, r0 + 64 + 2 * lane + 1};
     double ux[NV][4], acc_row[NV][4];
+    // COH: the staging loads are issued here but only consumed (stored to shared memory) behind the loads of the
+    // first tile, so the strip does not start with an exposed L2 round trip
+    double stg[2] = {0.0, 0.0};
+    bool staged = !COH;
     if (COH) {
-        for (int idx = threadIdx.x; idx < SW * TC + TR; idx += blockDim.x) {
-            long long g;
-            if (idx < SW * TC) g = (long long)(sc * P.sw * TC + idx) * P.py + P.y;    // column idx of the strip
-            else g = (long long)(r0 + idx - SW * TC) * P.px + P.x;                     // row of the tile row
-            su[idx] = (g < P.L) ? ldu<true>(P, io.u[0], g) : 0.0;
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int idx = threadIdx.x + q * 256;
+            if (idx < SW * TC + TR) {
+                long long g;
+                if (idx < SW * TC) g = (long long)(sc * P.sw * TC + idx) * P.py + P.y;    // column idx of the strip
+                else g = (long long)(r0 + idx - SW * TC) * P.px + P.x;                     // row of the tile row
+                stg[q] = (g < P.L) ? ldu<true>(P, io.u[0], g) : 0.0;
+            }
         }
-        __syncthreads();
     }
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         long long g = (long long)rloc[q] * P.px + P.x;
 #pragma unroll
         for (int v = 0; v < NV; v++) {
-            if (COH) ux[v][q] = su[SW * TC + rloc[q] - r0];
-            else ux[v][q] = (g < P.L) ? ldu<COH>(P, io.u[v], g) : 0.0;
+            ux[v][q] = (!COH && g < P.L) ? ldu<COH>(P, io.u[v], g) : 0.0;
             acc_row[v][q] = 0.0;
         }
     }
@@ -172,6 +178,14 @@ __device__ __forceinline__ void symv_strip(const TrdP &P, const SymvIO<NV> &io, 
         for (int c = 0; c < 8; c++) {
             v0[c] = __ldcs(reinterpret_cast<const double2 *>(base + (size_t)c * P.lda));
             v1[c] = __ldcs(reinterpret_cast<const double2 *>(base + (size_t)c * P.lda + 64));
+        }
+        if (COH && !staged) {
+            su[threadIdx.x] = stg[0];
+            if (threadIdx.x + 256 < SW * TC + TR) su[threadIdx.x + 256] = stg[1];
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 4; q++) ux[0][q] = su[SW * TC + rloc[q] - r0];
+            staged = true;
         }
         const long long cmin_g = (long long)c0 * P.py + P.y;
         const long long cmax_g = (long long)(c0 + TC - 1) * P.py + P.y;
@@ -269,6 +283,7 @@ __device__ void dots_chunk(const TrdP &P, const double *const *uvec, int first_s
         double s[NV];
 #pragma unroll
         for (int v = 0; v < NV; v++) s[v] = 0.0;
+#pragma unroll 4
         for (int j = j0 + lane; j < j1; j += 32) {
             const double cj = ldv<COH>(col + j);
 #pragma unroll
@@ -801,7 +816,8 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
         gy = block_max_int<256>(gy, s_redi);
         for (int s_ = tid; s_ < nsc && s_ < 1024; s_ += 256) s_nbr[s_] = strip_rows(Q, s_, nclL);
         const long long ntile = (long long)gx * gy;
-        const long long nitems = ntile + (ndone > 0 ? NCH : 0);
+        const long long ndots = ndone > 0 ? NCH : 0;
+        const long long nitems = ntile + ndots;
         if (timing) t_mark = globaltimer_ns();
         // ================= [S] SYMV tiles + panel dot products =================================================
         {
@@ -816,11 +832,13 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
                 const long long item = s_item;
                 if (item >= nitems) break;
                 if (tid == 0) next = (long long)(atomicAdd(C.work, 1ull) - work_base);   // in flight during the strip
-                if (item < ntile) {
+                // the panel dot products come FIRST in ticket order: they are latency-bound (one CTA per row chunk)
+                // and must run next to the tiles, not behind them
+                if (item >= ndots) {
                     int sc, br;
-                    if (fold_triangle(Q, (int)item, gx, nclL, sc, br)) symv_strip<1, true>(Q, io, br, sc, nclL, smem, s_u);
+                    if (fold_triangle(Q, (int)(item - ndots), gx, nclL, sc, br)) symv_strip<1, true>(Q, io, br, sc, nclL, smem, s_u);
                 } else {
-                    dots_chunk<1, true>(Q, uv, k + 1, (int)(item - ntile));
+                    dots_chunk<1, true>(Q, uv, k + 1, (int)item);
                 }
                 __syncthreads();
             }
