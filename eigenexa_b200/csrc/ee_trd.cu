@@ -59,6 +59,7 @@ struct TrdP {
     int has_next;                       // vvec: build next column
     int first;                          // vvec: panel prologue only (no v to form)
     int piv; double upiv;               // persistent kernel: u(piv) is upiv (not yet visible in ucur), piv = -1: none
+    int sv;                             // persistent kernel: tile rows per work item (column partials are summed over them)
 };
 
 // Loads of vectors that other CTAs write during the same launch (persistent panel kernel) must bypass the
@@ -131,9 +132,11 @@ struct SymvIO {
 // COH (persistent kernel, NV = 1): the entries of u this strip needs -- SW*TC columns, TR rows -- are staged in
 // shared memory (su) with coalesced ld.global.cg loads up front: a coherent load inside the column loop would
 // be an L2 round trip per column on the critical path.
+// scol != nullptr (persistent kernel): the column sums are added to scol[SW*TC] (every entry belongs to one thread)
+// instead of being written to Pcol -- the caller sweeps several tile rows and writes one partial per column.
 template <int NV, bool COH = false>
 __device__ __forceinline__ void symv_strip(const TrdP &P, const SymvIO<NV> &io, int br, int sc, int nclL, double *smem,
-                                           double *su = nullptr)
+                                           double *su = nullptr, double *scol = nullptr)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r0 = br * TR;
@@ -244,7 +247,8 @@ __device__ __forceinline__ void symv_strip(const TrdP &P, const SymvIO<NV> &io, 
             r += __shfl_xor_sync(0xffffffffu, r, 1);
             if ((lane & 3) == 0) {
                 int c = (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0);
-                io.pcol[v][(size_t)br * P.ldpcol + cw + c] = r;
+                if (COH && scol) scol[st * TC + 8 * warp + c] += r;
+                else io.pcol[v][(size_t)br * P.ldpcol + cw + c] = r;
             }
         }
     }
@@ -325,6 +329,20 @@ __device__ __forceinline__ bool fold_triangle(const TrdP &P, int bid, int gx, in
     if (sc2 == sc1) return false;
     br = by - n1; sc = sc2;
     return br < strip_rows(P, sc2, nclL);
+}
+
+// same with work items of P.sv tile rows: item (sc, bg) covers the tile rows bg*sv .. bg*sv+sv-1 of strip sc
+__device__ __forceinline__ int strip_groups(const TrdP &P, int sc, int nclL) { return (strip_rows(P, sc, nclL) + P.sv - 1) / P.sv; }
+__device__ __forceinline__ bool fold_triangle_g(const TrdP &P, int bid, int gx, int nclL, int &sc, int &bg)
+{
+    const int nsc = nstrips_of(P, nclL);
+    const int bx = bid % gx, by = bid / gx;
+    const int sc1 = nsc - 1 - bx, sc2 = bx;
+    const int n1 = strip_groups(P, sc1, nclL);
+    if (by < n1) { sc = sc1; bg = by; return true; }
+    if (sc2 == sc1) return false;
+    bg = by - n1; sc = sc2;
+    return bg < strip_groups(P, sc2, nclL);
 }
 
 __global__ void __launch_bounds__(256, 2) symv_kernel(TrdP P, int gx, int ntile_blocks)
@@ -437,9 +455,9 @@ __global__ void __launch_bounds__(VR * VS) pvec_kernel(TrdP P, PeerView pv, unsi
     }
     if (MODE == 1) return;
     if (MODE == 3) {
-        __threadfence_system();
+        // one system-scope release per CTA (bar.sync orders the CTA's peer stores before it; the fence is cumulative)
         __syncthreads();
-        if (threadIdx.x == 0) s_last = atomicAdd(&P.tickets[3], 1u);
+        if (threadIdx.x == 0) { __threadfence_system(); s_last = atomicAdd(&P.tickets[3], 1u); }
         __syncthreads();
         if (s_last == gridDim.x - 1 && threadIdx.x == 0) {
             __threadfence_system();
@@ -628,12 +646,16 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     return t;
 }
 
-// all CTAs of the (co-resident) grid; target = number of arrivals that completes this barrier
+// all CTAs of the (co-resident) grid; target = number of arrivals that completes this barrier.
+// SYS: the CTA's earlier stores include NVLink stores to peer memory -- thread 0 releases them at system scope.
+// One fence per CTA: bar.sync orders the CTA's stores before thread 0's fence and the fence is cumulative; a
+// fence.sc.sys executed by every thread serialises inside the SM and costs ~30 us per column.
+template <bool SYS = false>
 __device__ __forceinline__ void grid_barrier(unsigned long long *bar, unsigned long long target)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
+        if (SYS) __threadfence_system(); else __threadfence();
         atomicAdd(bar, 1ull);
         unsigned int spins = 0;
         while (ld_acquire_gpu(bar) < target) {
@@ -681,6 +703,7 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
     __shared__ int s_nbr[1024];
     __shared__ double s_ur[MAXM], s_vr[MAXM];
     __shared__ double s_u[SW * TC + TR];     // entries of u of the strip in flight
+    __shared__ double s_col[SW * TC];        // column sums of the work item in flight (summed over its tile rows)
     __shared__ double s_red[8];
     __shared__ int s_redi[8];
     __shared__ long long s_item;
@@ -804,13 +827,16 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
         const int nclL = cyc_count(L, P.py, P.y);
         const int sw = (L > 12288) ? 4 : (L > 6144) ? 2 : 1;
         Q.sw = sw;
+        // tile rows per work item: the column partials the p phase has to sum shrink by this factor (at L = 50000
+        // they are 2/3 of the 230 MB of partials per column); small trailing matrices keep fine-grained items
+        Q.sv = sw;
         const int nsc = (nclL + sw * TC - 1) / (sw * TC);
         const int gx = (nsc + 1) / 2;
-        // rows of the biggest strip + rows of the smallest (fold_triangle), max over the CTA columns
+        // groups of the biggest strip + groups of the smallest (fold_triangle_g), max over the CTA columns
         int gy = 0;
         for (int bx = tid; bx < gx; bx += 256) {
             const int s1 = nsc - 1 - bx, s2 = bx;
-            int rr = strip_rows(Q, s1, nclL) + (s2 != s1 ? strip_rows(Q, s2, nclL) : 0);
+            int rr = strip_groups(Q, s1, nclL) + (s2 != s1 ? strip_groups(Q, s2, nclL) : 0);
             gy = max(gy, rr);
         }
         gy = block_max_int<256>(gy, s_redi);
@@ -835,8 +861,19 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
                 // the panel dot products come FIRST in ticket order: they are latency-bound (one CTA per row chunk)
                 // and must run next to the tiles, not behind them
                 if (item >= ndots) {
-                    int sc, br;
-                    if (fold_triangle(Q, (int)(item - ndots), gx, nclL, sc, br)) symv_strip<1, true>(Q, io, br, sc, nclL, smem, s_u);
+                    int sc, bg;
+                    if (fold_triangle_g(Q, (int)(item - ndots), gx, nclL, sc, bg)) {
+                        // this thread's column-sum slots: (lane & 3) == 0 owns column 8 warp + c of every tile
+                        const int lane_ = tid & 31, warp_ = tid >> 5;
+                        const int cown = ((lane_ & 16) ? 4 : 0) + ((lane_ & 8) ? 2 : 0) + ((lane_ & 4) ? 1 : 0);
+                        if ((lane_ & 3) == 0)
+                            for (int t_ = 0; t_ < sw; t_++) s_col[t_ * TC + 8 * warp_ + cown] = 0.0;
+                        const int br_end = min(bg * Q.sv + Q.sv, strip_rows(Q, sc, nclL));
+                        for (int br = bg * Q.sv; br < br_end; br++) symv_strip<1, true>(Q, io, br, sc, nclL, smem, s_u, s_col);
+                        if ((lane_ & 3) == 0)
+                            for (int t_ = 0; t_ < sw; t_++)
+                                P.Pcol[(size_t)bg * P.ldpcol + (size_t)(sc * sw + t_) * TC + 8 * warp_ + cown] = s_col[t_ * TC + 8 * warp_ + cown];
+                    }
                 } else {
                     dots_chunk<1, true>(Q, uv, k + 1, (int)item);
                 }
@@ -875,7 +912,7 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
                 }
                 if (coln) {
                     const int il = g / P.py;
-                    const int nb = ntile_rows(Q, il / TC, nclL);
+                    const int nb = (ntile_rows(Q, il / TC, nclL) + Q.sv - 1) / Q.sv;     // groups of tile rows
 #pragma unroll 4
                     for (int b = sl; b < nb; b += VS) acc += __ldcg(P.Pcol + (size_t)b * P.ldpcol + il);
                     if (rown && sl == 0) acc = fma(P.A[(size_t)il * P.lda + g / P.px], ldu<true>(Q, ucur, g), acc);
@@ -926,8 +963,7 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
                     for (int q = 0; q < pv.P; q++) pv.slots[q][off] = p;
                 }
             }
-            __threadfence_system();
-            grid_barrier(C.bar, (++nbar) * (unsigned long long)G);
+            grid_barrier<true>(C.bar, (++nbar) * (unsigned long long)G);
             if (bid == 0 && tid == 0) {
                 __threadfence_system();
                 for (int q = 0; q < pv.P; q++) st_release_sys(pv.flags[q] + (size_t)par * pv.P + pv.r, epoch);
@@ -1398,9 +1434,9 @@ __global__ void __launch_bounds__(VR * VS) pvec2_kernel(PrdP P, PeerView pv, uns
     }
     if (MODE == 1) return;
     if (MODE == 3) {
-        __threadfence_system();
+        // one system-scope release per CTA (bar.sync orders the CTA's peer stores before it; the fence is cumulative)
         __syncthreads();
-        if (threadIdx.x == 0) s_last = atomicAdd(&P.tickets[3], 1u);
+        if (threadIdx.x == 0) { __threadfence_system(); s_last = atomicAdd(&P.tickets[3], 1u); }
         __syncthreads();
         if (s_last == gridDim.x - 1 && threadIdx.x == 0) {
             __threadfence_system();
