@@ -25,13 +25,21 @@ void set_error(const char *fmt, ...)
     va_end(ap);
     fprintf(stderr, "[eigenexa_b200] %s\n", g_err);
 }
+// Allocation / device / NCCL failures.  The reference aborts the job (eigen_abort -> MPI_Abort,
+// eigen_devel.F:148-164); a shared library must not take the host application down, so the failure unwinds to
+// the C-ABI entry point, which reports it (eigen_get_errinfo -> -1, eigenexa_b200_last_error, w = NaN for the
+// drivers) and returns.  EIGENEXA_B200_ABORT_ON_ERROR=1 restores the reference's abort.
 void fatal(const char *what, const char *file, int line)
 {
-    // allocation / device failures abort the job like eigen_abort -> MPI_Abort (eigen_devel.F:148-164)
-    fprintf(stderr, "[eigenexa_b200] FATAL %s (%s:%d)\n", what, file, line);
+    snprintf(g_err, sizeof g_err, "FATAL %s (%s:%d)", what, file, line);
+    fprintf(stderr, "[eigenexa_b200] %s\n", g_err);
     fflush(stderr);
-    abort();
+    const char *e = getenv("EIGENEXA_B200_ABORT_ON_ERROR");
+    if (e && e[0] == '1') abort();
+    throw FatalError();
 }
+#define EE_TRY try {
+#define EE_CATCH(stmt) } catch (const ::ee::FatalError &) { ::ee::ctx().errinfo = -1; stmt; }
 
 Context &ctx()
 {
@@ -160,7 +168,16 @@ struct StageTimer {
 };
 
 // eigen_s0 / eigen_FS sequencing (src/eigen_s.F:81-305).  dev_ptrs: a,w,z are device pointers.
+static void eigen_s_body(int n, int nvec, double *a, int lda, double *w, double *z, int ldz, int m_forward,
+                         int m_backward, const char *mode_in, bool dev_ptrs, bool penta);
 static void eigen_s_impl(int n, int nvec, double *a, int lda, double *w, double *z, int ldz, int m_forward,
+                         int m_backward, const char *mode_in, bool dev_ptrs, bool penta)
+{
+    EE_TRY
+    eigen_s_body(n, nvec, a, lda, w, z, ldz, m_forward, m_backward, mode_in, dev_ptrs, penta);
+    EE_CATCH(if (!dev_ptrs && w && n > 0) for (int i = 0; i < n; i++) w[i] = NAN)
+}
+static void eigen_s_body(int n, int nvec, double *a, int lda, double *w, double *z, int ldz, int m_forward,
                          int m_backward, const char *mode_in, bool dev_ptrs, bool penta)
 {
     Context &c = ctx();
@@ -304,10 +321,11 @@ using namespace ee;
 
 extern "C" {
 
-int eigenexa_b200_get_unique_id(unsigned char *id) { return comm_get_unique_id(id); }
+int eigenexa_b200_get_unique_id(unsigned char *id)
+try { return comm_get_unique_id(id); } catch (const ::ee::FatalError &) { return 99; }
 
 void eigen_init(const eigenexa_b200_comm_t *comm, const char *order)
-{
+try {
     Context &c = ctx();
     if (c.initialized) {
         // eigen_init twice: warning + implicit free (eigen_libs0.F:327-339)
@@ -347,10 +365,10 @@ void eigen_init(const eigenexa_b200_comm_t *comm, const char *order)
     pool_create(c.device);
     if (comm_init(comm ? comm->unique_id : nullptr, rank, nranks, g) != 0) return;
     c.initialized = true;
-}
+} catch (const ::ee::FatalError &) { ::ee::ctx().errinfo = -1; }
 
 void eigen_free(void)
-{
+try {
     Context &c = ctx();
     if (!c.initialized) return;
     cudaStreamSynchronize(c.stream);
@@ -362,7 +380,7 @@ void eigen_free(void)
     cudaStreamDestroy(c.stream); cudaStreamDestroy(c.stream2);
     c.stream = c.stream2 = nullptr;
     c.initialized = false;
-}
+} catch (const ::ee::FatalError &) { ::ee::ctx().errinfo = -1; }
 
 void eigen_s(int n, int nvec, double *a, int lda, double *w, double *z, int ldz, int m_forward, int m_backward,
              const char *mode)
@@ -376,18 +394,18 @@ void eigen_sx(int n, int nvec, double *a, int lda, double *w, double *z, int ldz
 }
 int eigenexa_b200_eigen_s_dev(int n, int nvec, double *a_dev, int lda, double *w_dev, double *z_dev, int ldz,
                               int m_forward, int m_backward, const char *mode)
-{
+try {
     if (!ctx().initialized) { set_error("not initialised"); return 1; }
     eigen_s_impl(n, nvec, a_dev, lda, w_dev, z_dev, ldz, m_forward, m_backward, mode, true, false);
     return 0;
-}
+} catch (const ::ee::FatalError &) { ::ee::ctx().errinfo = -1; return 99; }
 int eigenexa_b200_eigen_sx_dev(int n, int nvec, double *a_dev, int lda, double *w_dev, double *z_dev, int ldz,
                                int m_forward, int m_backward, const char *mode)
-{
+try {
     if (!ctx().initialized) { set_error("not initialised"); return 1; }
     eigen_s_impl(n, nvec, a_dev, lda, w_dev, z_dev, ldz, m_forward, m_backward, mode, true, true);
     return 0;
-}
+} catch (const ::ee::FatalError &) { ::ee::ctx().errinfo = -1; return 99; }
 
 void eigen_get_version(int *version, char *date, char *vcode)
 {
@@ -548,7 +566,7 @@ int eigen_blacs_eigen_get_blacs_context_(void) { return -1; }
 
 // ---- stage-level entry points ---------------------------------------------------------------
 int eigenexa_b200_trd(int n, double *a, int lda, double *d, double *e, int m_forward)
-{
+try {
     Context &c = ctx();
     if (!c.initialized) { set_error("not initialised"); return 1; }
     if (n <= 0) return 2;
@@ -569,7 +587,7 @@ int eigenexa_b200_trd(int n, double *a, int lda, double *d, double *e, int m_for
     EE_CUDA(cudaStreamSynchronize(c.stream));
     dev_free(a_d); dev_free(d_d); dev_free(e_d);
     return 0;
-}
+} catch (const ::ee::FatalError &) { ::ee::ctx().errinfo = -1; return 99; }
 
 int eigenexa_b200_trbakwy_nb(int n, int nvec, const double *a, int lda, double *z, int ldz, const double *e,
                              int m_backward, int nb);
@@ -580,7 +598,7 @@ int eigenexa_b200_trbakwy(int n, int nvec, const double *a, int lda, double *z, 
 
 int eigenexa_b200_trbakwy_nb(int n, int nvec, const double *a, int lda, double *z, int ldz, const double *e,
                              int m_backward, int nb)
-{
+try {
     Context &c = ctx();
     if (!c.initialized) { set_error("not initialised"); return 1; }
     if (n <= 0 || nvec <= 0) return 2;
@@ -604,11 +622,11 @@ int eigenexa_b200_trbakwy_nb(int n, int nvec, const double *a, int lda, double *
     EE_CUDA(cudaStreamSynchronize(c.stream));
     dev_free(a_d); dev_free(z_d); dev_free(e_d);
     return 0;
-}
+} catch (const ::ee::FatalError &) { ::ee::ctx().errinfo = -1; return 99; }
 
 // eigen_prd(n, a, lda, d, e, ne, m)  (src/eigen_prd.F:80): e is (ne x 2), e(:,1) first, e(:,2) second off-diagonal
 int eigenexa_b200_prd(int n, double *a, int lda, double *d, double *e, int ne, int m_forward)
-{
+try {
     Context &c = ctx();
     if (!c.initialized) { set_error("not initialised"); return 1; }
     if (n <= 0) return 2;
@@ -630,11 +648,11 @@ int eigenexa_b200_prd(int n, double *a, int lda, double *d, double *e, int ne, i
     EE_CUDA(cudaStreamSynchronize(c.stream));
     dev_free(a_d); dev_free(d_d); dev_free(e_d);
     return 0;
-}
+} catch (const ::ee::FatalError &) { ::ee::ctx().errinfo = -1; return 99; }
 
 // eigen_dcx (src/dcx.F:75): penta-diagonal (d, e(:,1), e(:,2)) -> w, z
 int eigenexa_b200_dcx(int n, int nvec, const double *d, const double *e, int ne, double *w, double *z, int ldz)
-{
+try {
     Context &c = ctx();
     if (!c.initialized) { set_error("not initialised"); return 1; }
     if (n <= 0 || ne < n) return 2;
@@ -657,11 +675,11 @@ int eigenexa_b200_dcx(int n, int nvec, const double *d, const double *e, int ne,
     EE_CUDA(cudaStreamSynchronize(c.stream));
     dev_free(z_d); dev_free(d_d); dev_free(e_d); dev_free(w_d);
     return info;
-}
+} catch (const ::ee::FatalError &) { ::ee::ctx().errinfo = -1; return 99; }
 
 // eigen_bisect2 (src/bisect2.F:71)
 int eigenexa_b200_bisect2(int n, const double *d, const double *e, int ne, double *w)
-{
+try {
     Context &c = ctx();
     if (!c.initialized) { set_error("not initialised"); return 1; }
     if (n <= 0 || ne < n) return 2;
@@ -675,10 +693,10 @@ int eigenexa_b200_bisect2(int n, const double *d, const double *e, int ne, doubl
     EE_CUDA(cudaStreamSynchronize(c.stream));
     dev_free(d_d); dev_free(e_d); dev_free(w_d);
     return 0;
-}
+} catch (const ::ee::FatalError &) { ::ee::ctx().errinfo = -1; return 99; }
 
 int eigenexa_b200_dc(int n, int nvec, const double *d, const double *e, double *w, double *z, int ldz)
-{
+try {
     Context &c = ctx();
     if (!c.initialized) { set_error("not initialised"); return 1; }
     if (n <= 0) return 2;
@@ -700,10 +718,10 @@ int eigenexa_b200_dc(int n, int nvec, const double *d, const double *e, double *
     EE_CUDA(cudaStreamSynchronize(c.stream));
     dev_free(z_d); dev_free(d_d); dev_free(e_d); dev_free(w_d);
     return info;
-}
+} catch (const ::ee::FatalError &) { ::ee::ctx().errinfo = -1; return 99; }
 
 int eigenexa_b200_bisect(int n, const double *d, const double *e, double *w)
-{
+try {
     Context &c = ctx();
     if (!c.initialized) { set_error("not initialised"); return 1; }
     if (n <= 0) return 2;
@@ -716,50 +734,54 @@ int eigenexa_b200_bisect(int n, const double *d, const double *e, double *w)
     EE_CUDA(cudaStreamSynchronize(c.stream));
     dev_free(d_d); dev_free(e_d); dev_free(w_d);
     return 0;
-}
+} catch (const ::ee::FatalError &) { ::ee::ctx().errinfo = -1; return 99; }
 
 int eigenexa_b200_mat_set_dev(int n, double *a_dev, int lda, int mtype, uint64_t seed)
-{
+try {
     if (!ctx().initialized) { set_error("not initialised"); return 1; }
     mat_set_dev(n, a_dev, lda, mtype, seed);
     EE_CUDA(cudaStreamSynchronize(ctx().stream));
     return 0;
-}
+} catch (const ::ee::FatalError &) { ::ee::ctx().errinfo = -1; return 99; }
 
 int eigenexa_b200_mat_set_host(int n, double *a, int lda, int mtype, uint64_t seed)
-{
+try {
     if (!ctx().initialized) { set_error("not initialised"); return 1; }
     mat_set_host(n, a, lda, mtype, seed, ctx().g);
     return 0;
-}
+} catch (const ::ee::FatalError &) { ::ee::ctx().errinfo = -1; return 99; }
 
 int eigenexa_b200_ev_test_dev(int n, int nvec, const double *a_dev, int lda, const double *w_dev, const double *z_dev,
                               int ldz, double *out)
-{
+try {
     if (!ctx().initialized) { set_error("not initialised"); return 1; }
     ev_test_dev(n, nvec, a_dev, lda, w_dev, z_dev, ldz, out);
     return 0;
-}
+} catch (const ::ee::FatalError &) { ::ee::ctx().errinfo = -1; return 99; }
 
 int eigenexa_b200_dgemm_dev(char transa, char transb, int m, int n, int k, double alpha, const double *a_dev, int lda,
                             const double *b_dev, int ldb, double beta, double *c_dev, int ldc)
-{
+try {
     if (!ctx().initialized) { set_error("not initialised"); return 1; }
     dgemm(ctx().stream, transa, transb, m, n, k, alpha, a_dev, lda, b_dev, ldb, beta, c_dev, ldc);
     return 0;
-}
+} catch (const ::ee::FatalError &) { ::ee::ctx().errinfo = -1; return 99; }
 // staircase form used by the trailing update of eigen_trd / eigen_prd: only tiles that reach the
 // upper triangle of the cyclic local matrix (global row jl*px+x <= global col il*py+y) are touched
 int eigenexa_b200_dgemm_tri_dev(char transa, char transb, int m, int n, int k, double alpha, const double *a_dev, int lda,
                                 const double *b_dev, int ldb, double beta, double *c_dev, int ldc, int px, int py, int x,
                                 int y)
-{
+try {
     if (!ctx().initialized) { set_error("not initialised"); return 1; }
     TriSpec tri; tri.mode = 1; tri.px = px; tri.py = py; tri.x = x; tri.y = y;
     dgemm(ctx().stream, transa, transb, m, n, k, alpha, a_dev, lda, b_dev, ldb, beta, c_dev, ldc, tri);
     return 0;
-}
-void eigenexa_b200_sync(void) { if (ctx().initialized) EE_CUDA(cudaStreamSynchronize(ctx().stream)); }
+} catch (const ::ee::FatalError &) { ::ee::ctx().errinfo = -1; return 99; }
+void eigenexa_b200_sync(void)
+try { if (ctx().initialized) EE_CUDA(cudaStreamSynchronize(ctx().stream)); } catch (const ::ee::FatalError &) { ::ee::ctx().errinfo = -1; }
+// test hook: raises the library's fatal-error path inside a guarded entry point (must return 99, not abort)
+int eigenexa_b200_debug_raise(void)
+try { ::ee::fatal("debug_raise", __FILE__, __LINE__); } catch (const ::ee::FatalError &) { ::ee::ctx().errinfo = -1; return 99; }
 void *eigenexa_b200_stream(void) { return (void *)ctx().stream; }
 
 int64_t eigenexa_b200_launch_count(int reset)

@@ -17,6 +17,7 @@ namespace ee {
 // error handling: the product fails loudly (no CPU fallback anywhere)
 // ---------------------------------------------------------------------------------------
 void set_error(const char *fmt, ...);
+struct FatalError {};   // thrown by fatal(), caught at every C-ABI entry point (ee_capi.cu)
 [[noreturn]] void fatal(const char *what, const char *file, int line);
 
 #define EE_CUDA(call)                                                                      \

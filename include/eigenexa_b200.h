@@ -190,6 +190,12 @@ int eigenexa_b200_symv_trace(float *out, int cap);
 /* profiling aid: eigen_trd stops after ncols columns (results are then meaningless); 0 = off */
 void eigenexa_b200_set_debug_maxcols(int ncols);
 const char *eigenexa_b200_last_error(void);
+/* Error convention on device / allocation / NCCL failures: the reference aborts the job (eigen_abort -> MPI_Abort,
+ * src/eigen_devel.F:148-164).  This library unwinds to the entry point instead: eigen_s / eigen_sx fill w with NaN,
+ * the int-returning entry points return 99, eigen_get_errinfo reports -1 and eigenexa_b200_last_error the message.
+ * EIGENEXA_B200_ABORT_ON_ERROR=1 in the environment restores abort().  eigenexa_b200_debug_raise exercises that
+ * path (test hook): it returns 99.                                                                                 */
+int eigenexa_b200_debug_raise(void);
 
 #ifdef __cplusplus
 }

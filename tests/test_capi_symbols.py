@@ -87,3 +87,13 @@ def test_no_gpu_means_loud_failure_not_cpu_fallback():
     w = np.full(n, 3.0); z = np.zeros((n, n), order="F")
     E.eigen_sx(n, a.copy(order="F"), w, z)
     assert np.all(w == 3.0)
+
+
+def test_fatal_errors_unwind_to_the_entry_point_instead_of_aborting():
+    """A device / allocation / NCCL failure must not abort() the host application (the reference calls MPI_Abort,
+    src/eigen_devel.F:148-164): the entry point returns 99, errinfo = -1, the message is kept."""
+    import eigenexa_b200 as E
+    L = E.lib()
+    assert L.eigenexa_b200_debug_raise() == 99
+    assert "debug_raise" in E.last_error()
+    assert E.eigen_get_errinfo() == -1
