@@ -825,11 +825,15 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
         Q.k = k; Q.L = L; Q.ndone = ndone; Q.ucur = ucur; Q.unext = unext;
         Q.piv = L - 1; Q.upiv = sc_un;
         const int nclL = cyc_count(L, P.py, P.y);
-        const int sw = (L > 12288) ? 4 : (L > 6144) ? 2 : 1;
+        // work item = sw tiles along a row strip x sv tile rows.  Long items amortise the row-sum exchange and
+        // shrink the partials the p phase has to sum (at L = 50000 on one GPU: 230 MB per column with 1-tile-row
+        // items); short ones keep >= ~6 items per CTA for the ticket scheduler when the LOCAL trailing matrix is small
+        const long long ntl = ((long long)cyc_count(L, P.px, P.x) / TR + 1) * ((long long)nclL / TC + 1) / 2;   // ~ local tiles
+        const long long per = ntl / (6LL * G);
+        const int sw = per >= 4 ? 4 : per >= 2 ? 2 : 1;
+        const int sv = per >= 16 ? 4 : per >= 8 ? 2 : 1;
         Q.sw = sw;
-        // tile rows per work item: the column partials the p phase has to sum shrink by this factor (at L = 50000
-        // they are 2/3 of the 230 MB of partials per column); small trailing matrices keep fine-grained items
-        Q.sv = sw;
+        Q.sv = sv;
         const int nsc = (nclL + sw * TC - 1) / (sw * TC);
         const int gx = (nsc + 1) / 2;
         // groups of the biggest strip + groups of the smallest (fold_triangle_g), max over the CTA columns
