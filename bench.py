@@ -298,7 +298,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(lib_stream)
     t0 = time.perf_counter()
-    stage = np.zeros(32)
+    stage = np.zeros(48)
     for _ in range(n_steps):
         step_dev()
         stage += E.last_timings()
@@ -382,6 +382,9 @@ def main():
               "fp64_tensor_peak_tflops": fp64_peak, "fp64_peak_source": "cuBLAS DGEMM 8192^3 measured on this pool"}
     if persist:
         stages.update({"panel_kernel_s": kern_s, "p_phase_s": float(stage[16]), "v_phase_s": float(stage[31])})
+        if world > 1:
+            stages.update({"p_partial_and_peer_stores_s": float(stage[32]), "p_grid_barrier_s": float(stage[33]),
+                           "p_flag_exchange_s": float(stage[34]), "p_sum_and_corrections_s": float(stage[35])})
 
     def make_line(e2e, cpu, check, partial):
         line = {

@@ -332,8 +332,8 @@ def launch_count(reset=False) -> int:
 
 
 def last_timings():
-    t = np.zeros(32)
-    lib().eigenexa_b200_last_timings(_dp(t), 32)
+    t = np.zeros(48)
+    lib().eigenexa_b200_last_timings(_dp(t), 48)
     return t
 
 

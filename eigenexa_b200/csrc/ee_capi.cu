@@ -792,7 +792,7 @@ int64_t eigenexa_b200_launch_count(int reset)
 }
 void eigenexa_b200_last_timings(double *t, int nt)
 {
-    for (int i = 0; i < nt && i < 32; i++) t[i] = ctx().timings[i];
+    for (int i = 0; i < nt && i < 48; i++) t[i] = ctx().timings[i];
 }
 /* per-column symv kernel milliseconds of the last eigen_trd (column n-1 first); returns count */
 int eigenexa_b200_symv_trace(float *out, int cap)

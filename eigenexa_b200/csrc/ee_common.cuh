@@ -66,7 +66,7 @@ struct Context {
     Comm *comm = nullptr;
     int errinfo = 0;
     int profiling = 0;  // 0 off; 1 async CUDA events around symv/syr2k launches; 2 sync per kernel class
-    double timings[32] = {0};
+    double timings[48] = {0};
     int sm_count = 148;
     int debug_maxcols = 0;              // > 0: eigen_trd stops after this many columns (profiling aid)
     std::vector<cudaEvent_t> ev_pool;   // reusable timing events (profiling level 1)

@@ -617,7 +617,8 @@ struct PanelCtl {
     unsigned long long *bar;     // grid barrier counter, zeroed by the host before the launch
     unsigned long long *work;    // work ticket counter, zeroed by the host before the launch
     double *partA, *partB;       // [gridDim.x] per-CTA partial sums (u^T p / next-column norm)
-    double *tacc;                // [4] accumulated nanoseconds: 0 SYMV phase, 1 p phase, 2 v phase (CTA 0), or nullptr
+    double *tacc;                // [8] accumulated nanoseconds (CTA 0): 0 SYMV phase, 1 p phase, 2 v phase; inside the p phase
+                                 //     on a grid: 3 partial + peer stores, 4 barrier, 5 flag exchange, 6 sum + corrections; or nullptr
     double *pivraw;              // [2] raw pivot / diagonal element of the next column (written before the barrier)
     int k_stop;                  // last slot to process (2 for the first panel, else 0)
     unsigned long long epoch0;   // peer epoch of the first column of this launch (multi-rank)
@@ -713,7 +714,7 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
     unsigned long long nbar = 0;             // barriers passed so far
     unsigned long long work_base = 0;        // tickets consumed by the finished columns
     const bool timing = (C.tacc != nullptr) && bid == 0 && tid == 0;
-    unsigned long long t_mark = 0;
+    unsigned long long t_mark = 0, t_sub = 0;
     double *ucur = P.ucur, *unext = P.unext;
     double sc_g = 0.0, sc_un = 0.0, sc_beta = 1.0;   // Householder scalars of the current column (replicated per CTA)
     const int r = tid & 31, sl = tid >> 5;
@@ -967,7 +968,9 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
                     for (int q = 0; q < pv.P; q++) pv.slots[q][off] = p;
                 }
             }
+            if (timing) { const unsigned long long t = globaltimer_ns(); C.tacc[3] += (double)(t - t_mark); t_sub = t; }
             grid_barrier<true>(C.bar, (++nbar) * (unsigned long long)G);
+            if (timing) { const unsigned long long t = globaltimer_ns(); C.tacc[4] += (double)(t - t_sub); t_sub = t; }
             if (bid == 0 && tid == 0) {
                 __threadfence_system();
                 for (int q = 0; q < pv.P; q++) st_release_sys(pv.flags[q] + (size_t)par * pv.P + pv.r, epoch);
@@ -983,6 +986,7 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
                 __threadfence_system();
             }
             __syncthreads();
+            if (timing) { const unsigned long long t = globaltimer_ns(); C.tacc[5] += (double)(t - t_sub); t_sub = t; }
             for (int rb = bid; rb * VR < L; rb += G) {
                 const int g = rb * VR + r;
                 double acc = 0.0;
@@ -1004,6 +1008,7 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
                 }
             }
         }
+        if (MULTI && timing) { const unsigned long long t = globaltimer_ns(); C.tacc[6] += (double)(t - t_sub); }
         if (tid == 0) C.partA[bid] = up_cta;
         grid_barrier(C.bar, (++nbar) * (unsigned long long)G);
         const double alpha = grid_sum<256>(C.partA, G, s_red) / (2.0 * sc_beta);   // u^T p / (2 beta)  (trd_t6_3.F:255-262)
@@ -1639,7 +1644,7 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
     const bool use_peer = multi && comm_peer_setup((size_t)2 * npad, &pv);
 
     // ---- persistent panel kernel (one cooperative launch per panel) unless switched off / debugging ----------
-    bool persist = (!multi || use_peer) && c.debug_maxcols == 0 && c.profiling < 2;
+    bool persist = (!multi || use_peer) && c.profiling < 2;
     {
         const char *e = getenv("EIGENEXA_B200_TRD_PERSIST");
         if (e && e[0] == '0') persist = false;
@@ -1657,7 +1662,7 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
         ctl.bar = reinterpret_cast<unsigned long long *>(ws + oCtl);
         ctl.work = ctl.bar + 1;
         ctl.tacc = c.profiling ? ws + oCtl + 4 : nullptr;
-        ctl.pivraw = ws + oCtl + 8;
+        ctl.pivraw = ws + oCtl + 12;
         ctl.partA = ws + oPartAB; ctl.partB = ctl.partA + 2048;
     }
 
@@ -1825,6 +1830,8 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
                 prof_end(t_syr2k, 2);
             }
         }
+        // profiling aid (ncu targets): stop after the panels that cover debug_maxcols columns
+        if (persist && c.debug_maxcols > 0 && n - i_base >= c.debug_maxcols) { col_end = 0; break; }
     }
     double tw2 = wall();
     if (c.profiling >= 2) { EE_CUDA(cudaStreamSynchronize(st)); tw2 = wall(); }
@@ -1841,7 +1848,7 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
     if (nrl > 0 && ncl > 0)
         EE_CUDA(cudaMemcpy2DAsync(a_user, (size_t)lda_user * sizeof(double), A, (size_t)lda * sizeof(double),
                                   (size_t)nrl * sizeof(double), ncl, cudaMemcpyDeviceToDevice, st));
-    double tacc_h[4] = {0, 0, 0, 0};
+    double tacc_h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (persist && ctl.tacc) EE_CUDA(cudaMemcpyAsync(tacc_h, ctl.tacc, sizeof tacc_h, cudaMemcpyDeviceToHost, st));
     EE_CUDA(cudaStreamSynchronize(st));
     if (use_peer) {
@@ -1869,6 +1876,7 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
         // persistent kernel: timings[5] is the event time of the panel kernels; the in-kernel split (globaltimer of
         // CTA 0 around the phases of every column) goes to [15] SYMV phase, [16] p phase, [31] v phase
         c.timings[15] = tacc_h[0] * 1e-9; c.timings[16] = tacc_h[1] * 1e-9; c.timings[31] = tacc_h[2] * 1e-9;
+        for (int i = 0; i < 4; i++) c.timings[32 + i] = tacc_h[3 + i] * 1e-9;   // p phase on a grid: stores, barrier, flags, sum
         c.timings[9] = tw1 - tw0; c.timings[10] = tw2 - tw1; c.timings[11] = tw3 - tw2; c.timings[12] = tw4 - tw3;
         cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     }
