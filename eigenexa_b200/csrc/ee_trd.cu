@@ -636,6 +636,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ double ld_relaxed_sys(const double *p)
+{
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
 {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -953,7 +959,10 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
                 }
             }
         } else {
-            // partial -> slot[par][my rank] of EVERY rank (NVLink stores)
+            // PULL exchange: the partial goes to this rank's OWN slot (local stores, device-scope barrier), an epoch flag
+            // tells every peer it is there, and every rank then reads the P slots over NVLink.  (Pushing the partial
+            // into every peer's memory needs a system-scope fence behind 400 KB of outstanding NVLink stores in
+            // every CTA: 8 us per barrier + 12 us per flag round, profiles/r02_persist_notes.md.)
             for (int rb = bid; rb * VR < L; rb += G) {
                 const int g = rb * VR + r;
                 const double acc = partial_p(g);
@@ -964,12 +973,11 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
                     double p = 0.0;
 #pragma unroll
                     for (int q = 0; q < VS; q++) p += s_acc[q][r];
-                    const size_t off = ((size_t)par * pv.P + pv.r) * pv.slot_doubles + g;
-                    for (int q = 0; q < pv.P; q++) pv.slots[q][off] = p;
+                    pv.slots[pv.r][((size_t)par * pv.P + pv.r) * pv.slot_doubles + g] = p;
                 }
             }
             if (timing) { const unsigned long long t = globaltimer_ns(); C.tacc[3] += (double)(t - t_mark); t_sub = t; }
-            grid_barrier<true>(C.bar, (++nbar) * (unsigned long long)G);
+            grid_barrier(C.bar, (++nbar) * (unsigned long long)G);
             if (timing) { const unsigned long long t = globaltimer_ns(); C.tacc[4] += (double)(t - t_sub); t_sub = t; }
             if (bid == 0 && tid == 0) {
                 __threadfence_system();
@@ -990,10 +998,11 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
             for (int rb = bid; rb * VR < L; rb += G) {
                 const int g = rb * VR + r;
                 double acc = 0.0;
-                if (sl == 0 && g < L) {
-                    const double *base = pv.slots[pv.r] + (size_t)par * pv.P * pv.slot_doubles + g;
-                    for (int q = 0; q < pv.P; q++) acc += __ldcg(base + (size_t)q * pv.slot_doubles);
-                }
+                // rank q's partial from rank q's memory; the slices take one rank each (independent NVLink loads) and
+                // the fixed-order sum over the slices below is the same on every rank
+                if (g < L)
+                    for (int q = sl; q < pv.P; q += VS)
+                        acc += ld_relaxed_sys(pv.slots[q] + ((size_t)par * pv.P + q) * pv.slot_doubles + g);
                 acc = corrections(g, acc);
                 __syncthreads();
                 s_acc[sl][r] = acc;
