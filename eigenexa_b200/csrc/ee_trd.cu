@@ -983,6 +983,21 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
                 __threadfence_system();
                 for (int q = 0; q < pv.P; q++) st_release_sys(pv.flags[q] + (size_t)par * pv.P + pv.r, epoch);
             }
+            // the panel corrections do not depend on the peers: they are formed while the flags travel (and while
+            // this rank waits for a slower peer) and parked in pbuf
+            for (int rb = bid; rb * VR < L; rb += G) {
+                const int g = rb * VR + r;
+                const double acc = corrections(g, 0.0);
+                __syncthreads();
+                s_acc[sl][r] = acc;
+                __syncthreads();
+                if (sl == 0 && g < L) {
+                    double cs = 0.0;
+#pragma unroll
+                    for (int q = 0; q < VS; q++) cs += s_acc[q][r];
+                    P.pbuf[g] = cs;
+                }
+            }
             if (tid == 0) {
                 const unsigned long long *fl = pv.flags[pv.r] + (size_t)par * pv.P;
                 for (int q = 0; q < pv.P; q++) {
@@ -995,15 +1010,22 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
             }
             __syncthreads();
             if (timing) { const unsigned long long t = globaltimer_ns(); C.tacc[5] += (double)(t - t_sub); t_sub = t; }
+            // rank q's partial from rank q's memory; the slices take one rank each (independent NVLink loads), the loads
+            // of the next row block are in flight while this one is reduced, and the fixed-order sum over the slices is
+            // the same on every rank
+            auto peer_part = [&](int rb) -> double {
+                const int g = rb * VR + r;
+                double a = 0.0;
+                if (rb * VR < L && g < L)
+                    for (int q = sl; q < pv.P; q += VS)
+                        a += ld_relaxed_sys(pv.slots[q] + ((size_t)par * pv.P + q) * pv.slot_doubles + g);
+                return a;
+            };
+            double nxt = peer_part(bid);
             for (int rb = bid; rb * VR < L; rb += G) {
                 const int g = rb * VR + r;
-                double acc = 0.0;
-                // rank q's partial from rank q's memory; the slices take one rank each (independent NVLink loads) and
-                // the fixed-order sum over the slices below is the same on every rank
-                if (g < L)
-                    for (int q = sl; q < pv.P; q += VS)
-                        acc += ld_relaxed_sys(pv.slots[q] + ((size_t)par * pv.P + q) * pv.slot_doubles + g);
-                acc = corrections(g, acc);
+                const double acc = nxt;
+                nxt = peer_part(rb + G);
                 __syncthreads();
                 s_acc[sl][r] = acc;
                 __syncthreads();
@@ -1012,7 +1034,7 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
 #pragma unroll
                     for (int q = 0; q < VS; q++) p += s_acc[q][r];
                     double up = 0.0;
-                    if (g < L) { P.pbuf[g] = p; up = ldu<true>(Q, ucur, g) * p; }
+                    if (g < L) { p += P.pbuf[g]; P.pbuf[g] = p; up = ldu<true>(Q, ucur, g) * p; }
                     up_cta += warp_sum(up);
                 }
             }
