@@ -1021,11 +1021,12 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
                         a += ld_relaxed_sys(pv.slots[q] + ((size_t)par * pv.P + q) * pv.slot_doubles + g);
                 return a;
             };
-            double nxt = peer_part(bid);
+            double a0 = peer_part(bid), a1 = peer_part(bid + G), a2 = peer_part(bid + 2 * G), a3 = peer_part(bid + 3 * G);
             for (int rb = bid; rb * VR < L; rb += G) {
                 const int g = rb * VR + r;
-                const double acc = nxt;
-                nxt = peer_part(rb + G);
+                const double acc = a0;
+                a0 = a1; a1 = a2; a2 = a3;
+                a3 = peer_part(rb + 4 * G);      // four row blocks of NVLink loads in flight
                 __syncthreads();
                 s_acc[sl][r] = acc;
                 __syncthreads();

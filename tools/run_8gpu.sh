@@ -1,0 +1,12 @@
+#!/bin/bash
+# One 8-GPU lease: the 8-rank parity cases, the headline bench on the 2x4 grid, config 5 (eigen_sx N = 100000 on 2x4).
+# usage (GPU box): bash tools/run_8gpu.sh
+mkdir -p gpurun_out
+echo "gpus: $(nvidia-smi -L | wc -l)"
+timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -x -q -k "8-" > gpurun_out/r02_multi8_tests.log 2>&1
+tail -4 gpurun_out/r02_multi8_tests.log
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29618"
+timeout 500 $TR bench.py --gpus 8 --steps 5 --warmup 3 --budget-s 230 > gpurun_out/r02_bench_n8.log 2> gpurun_out/r02_bench_n8.err
+tail -c 1500 gpurun_out/r02_bench_n8.log; tail -2 gpurun_out/r02_bench_n8.err
+timeout 600 $TR bench.py --solver sx --n 100000 --gpus 8 --steps 1 --warmup 1 --budget-s 330 --no-e2e > gpurun_out/r02_bench_sx_n100000_8.log 2> gpurun_out/r02_bench_sx_n100000_8.err
+tail -c 1500 gpurun_out/r02_bench_sx_n100000_8.log; tail -2 gpurun_out/r02_bench_sx_n100000_8.err
