@@ -751,34 +751,42 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
         const int top = first ? L : c;
         const int nrows = first ? L + 1 : L;
         double nrm_cta = 0.0;
-        for (int rb = bid; rb * VR < nrows; rb += G) {
+        // loads + FMAs of one row block (no block barrier inside): the NEXT block's are issued before the current block is
+        // reduced, so two blocks of L2 latency overlap
+        struct VRow { double ug, vg, acc; };
+        auto v_rows = [&](int rb) -> VRow {
+            VRow o = {0.0, 0.0, 0.0};
             const int g = rb * VR + r;
-            double acc = 0.0;
-            if (g < nrows) {
-                double ug = 0.0, vg = 0.0;
+            if (rb * VR < nrows && g < nrows) {
                 if (!first) {
-                    ug = __ldcg(u_c + g);
-                    vg = (__ldcg(P.pbuf + g) - alpha * ug) / beta;
-                    if (sl == 0) {
-                        P.U[(size_t)k * P.npad + g] = ug;
-                        P.V[(size_t)k * P.npad + g] = vg;
-                    }
+                    o.ug = __ldcg(u_c + g);
+                    o.vg = (__ldcg(P.pbuf + g) - alpha * o.ug) / beta;
                 }
                 if (has_next && g <= top) {
-                    if (sl == 0) acc = __ldcg(P.W + (size_t)kn * P.npad + g);
+                    if (sl == 0) o.acc = __ldcg(P.W + (size_t)kn * P.npad + g);
                     for (int l = sl; l < nl; l += VS) {
                         const int slot = lo + l;
                         double uj, vj;
-                        if (!first && slot == k) { uj = ug; vj = vg; }
+                        if (!first && slot == k) { uj = o.ug; vj = o.vg; }
                         else { uj = __ldcg(P.U + (size_t)slot * P.npad + g); vj = __ldcg(P.V + (size_t)slot * P.npad + g); }
-                        acc = fma(-uj, s_vr[l], acc);
-                        acc = fma(-vj, s_ur[l], acc);
+                        o.acc = fma(-uj, s_vr[l], o.acc);
+                        o.acc = fma(-vj, s_ur[l], o.acc);
                     }
                 }
             }
+            return o;
+        };
+        VRow cur = v_rows(bid);
+        for (int rb = bid; rb * VR < nrows; rb += G) {
+            const int g = rb * VR + r;
+            const VRow nx = v_rows(rb + G);
+            if (!first && sl == 0 && g < nrows) {
+                P.U[(size_t)k * P.npad + g] = cur.ug;
+                P.V[(size_t)k * P.npad + g] = cur.vg;
+            }
             if (has_next) {
                 __syncthreads();
-                s_acc[sl][r] = acc;
+                s_acc[sl][r] = cur.acc;
                 __syncthreads();
                 if (sl == 0) {
                     double a = 0.0;
@@ -795,6 +803,7 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
                     nrm_cta += nrm;      // lane-uniform after warp_sum
                 }
             }
+            cur = nx;
         }
         if (!has_next) return;
         if (tid == 0) C.partB[bid] = nrm_cta;
@@ -942,10 +951,12 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
             return acc;
         };
         if (!MULTI) {
+            double nxt_p = (bid * VR < L) ? corrections(bid * VR + r, partial_p(bid * VR + r)) : 0.0;
             for (int rb = bid; rb * VR < L; rb += G) {
                 const int g = rb * VR + r;
-                double acc = partial_p(g);
-                acc = corrections(g, acc);
+                const double acc = nxt_p;
+                // the next row block's loads are in flight while this one is reduced
+                nxt_p = ((rb + G) * VR < L) ? corrections((rb + G) * VR + r, partial_p((rb + G) * VR + r)) : 0.0;
                 __syncthreads();
                 s_acc[sl][r] = acc;
                 __syncthreads();
@@ -963,9 +974,11 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
             // tells every peer it is there, and every rank then reads the P slots over NVLink.  (Pushing the partial
             // into every peer's memory needs a system-scope fence behind 400 KB of outstanding NVLink stores in
             // every CTA: 8 us per barrier + 12 us per flag round, profiles/r02_persist_notes.md.)
+            double nxt_p = (bid * VR < L) ? partial_p(bid * VR + r) : 0.0;
             for (int rb = bid; rb * VR < L; rb += G) {
                 const int g = rb * VR + r;
-                const double acc = partial_p(g);
+                const double acc = nxt_p;
+                nxt_p = ((rb + G) * VR < L) ? partial_p((rb + G) * VR + r) : 0.0;    // in flight during the reduction
                 __syncthreads();
                 s_acc[sl][r] = acc;
                 __syncthreads();
@@ -979,15 +992,19 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
             if (timing) { const unsigned long long t = globaltimer_ns(); C.tacc[3] += (double)(t - t_mark); t_sub = t; }
             grid_barrier(C.bar, (++nbar) * (unsigned long long)G);
             if (timing) { const unsigned long long t = globaltimer_ns(); C.tacc[4] += (double)(t - t_sub); t_sub = t; }
-            if (bid == 0 && tid == 0) {
+            // one thread per peer: P release stores in a row by one thread cost ~1.5 us each (every release waits for
+            // the previous store's acknowledgement), 12 us per column on 8 GPUs
+            if (bid == 0 && tid < pv.P) {
                 __threadfence_system();
-                for (int q = 0; q < pv.P; q++) st_release_sys(pv.flags[q] + (size_t)par * pv.P + pv.r, epoch);
+                st_release_sys(pv.flags[tid] + (size_t)par * pv.P + pv.r, epoch);
             }
             // the panel corrections do not depend on the peers: they are formed while the flags travel (and while
             // this rank waits for a slower peer) and parked in pbuf
+            double nxt_c = (bid * VR < L) ? corrections(bid * VR + r, 0.0) : 0.0;
             for (int rb = bid; rb * VR < L; rb += G) {
                 const int g = rb * VR + r;
-                const double acc = corrections(g, 0.0);
+                const double acc = nxt_c;
+                nxt_c = ((rb + G) * VR < L) ? corrections((rb + G) * VR + r, 0.0) : 0.0;
                 __syncthreads();
                 s_acc[sl][r] = acc;
                 __syncthreads();
@@ -998,13 +1015,11 @@ __global__ void __launch_bounds__(256, 2) trd_panel_kernel(TrdP P, PeerView pv, 
                     P.pbuf[g] = cs;
                 }
             }
-            if (tid == 0) {
-                const unsigned long long *fl = pv.flags[pv.r] + (size_t)par * pv.P;
-                for (int q = 0; q < pv.P; q++) {
-                    unsigned int spins = 0;
-                    while (ld_acquire_sys(fl + q) < epoch) {
-                        if (++spins > (1u << 27)) { *pv.err = 1; __trap(); }   // a peer never arrived
-                    }
+            if (tid < pv.P) {       // one poller per peer
+                const unsigned long long *fl = pv.flags[pv.r] + (size_t)par * pv.P + tid;
+                unsigned int spins = 0;
+                while (ld_acquire_sys(fl) < epoch) {
+                    if (++spins > (1u << 27)) { *pv.err = 1; __trap(); }   // a peer never arrived
                 }
                 __threadfence_system();
             }
