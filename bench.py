@@ -150,7 +150,15 @@ def cpu_oracle_leg(n_s, steps=1, warmup=0, budget_s=None):
 
 
 def workload_name(sname, n):
-    return f"{sname} N={n} random symmetric FP64, all eigenpairs (BASELINE configs[3])"
+    if sname == "eigen_s" and n == 50000:
+        tag = "BASELINE configs[3], the headline"
+    elif sname == "eigen_sx" and n == 100000:
+        tag = "BASELINE configs[4]"
+    elif sname == "eigen_s" and n == 10000:
+        tag = "BASELINE configs[1]"
+    else:
+        tag = "same family as BASELINE configs[3]"
+    return f"{sname} N={n} random symmetric FP64, all eigenpairs ({tag})"
 
 
 def run_reference(args):
