@@ -242,21 +242,25 @@ static void eigen_s_body(int n, int nvec, double *a, int lda, double *w, double 
         else trd_dev(n, a_d, lda_d, (mode == 'N') ? d_d : w_d, e_d, m_f);
         ret1 = (double)n * n * n * 4.0 / 3.0;
         T.mark(2);
-        if (!dev_ptrs && nrl > 0 && ncl > 0) {
-            // a on exit holds the Householder reflectors like the reference's (src/eigen_trd_t7.F:208, SURVEY 8(b)
-            // "a is clobbered"): copied back on the side stream while the tridiagonal stage runs (no PCIe use there)
+        // a on exit holds the Householder reflectors like the reference's (src/eigen_trd_t7.F:208, SURVEY 8(b) "a is
+        // clobbered"): copied back on the side stream.  It is queued when the BACK-TRANSFORMATION starts (GEMM-bound,
+        // no host traffic of its own): behind eigen_trd it would occupy the D2H copy engine for 0.8 s and stall the
+        // many small device-to-host copies of the divide & conquer.
+        auto copy_a_back = [&]() {
+            if (dev_ptrs || nrl <= 0 || ncl <= 0 || a_copied_back) return;
             EE_CUDA(cudaEventRecord(c.ev_side, st));
-            EE_CUDA(cudaStreamWaitEvent(c.stream2, c.ev_side, 0));
-            if (lda == ldd) EE_CUDA(cudaMemcpyAsync(a, a_d, (size_t)ldd * ncl * sizeof(double), cudaMemcpyDeviceToHost, c.stream2));
+            EE_CUDA(cudaStreamWaitEvent(c.stream3, c.ev_side, 0));
+            if (lda == ldd) EE_CUDA(cudaMemcpyAsync(a, a_d, (size_t)ldd * ncl * sizeof(double), cudaMemcpyDeviceToHost, c.stream3));
             else EE_CUDA(cudaMemcpy2DAsync(a, (size_t)lda * sizeof(double), a_d, (size_t)ldd * sizeof(double),
-                                           (size_t)nrl * sizeof(double), ncl, cudaMemcpyDeviceToHost, c.stream2));
+                                           (size_t)nrl * sizeof(double), ncl, cudaMemcpyDeviceToHost, c.stream3));
             a_copied_back = true;
-        }
+        };
         if (mode == 'N') {
             // eigen_bisect(d,e,w,n,0); NB the reference jumps to the exit without undoing
             // the scaling in this mode (eigen_s.F:219-234) -- kept.
             if (penta) bisect2_dev(n, d_d, e_d, e2_d, w_d);   // eigen_bisect2 (eigen_sx.F:219-221)
             else bisect_dev(n, d_d, e_d, w_d);
+            copy_a_back();
             T.mark(3); T.mark(4);
         } else {
             // ---- tridiagonal eigensolver (eigen_s.F:197-213) ---------------------------------
@@ -269,6 +273,7 @@ static void eigen_s_body(int n, int nvec, double *a, int lda, double *w, double 
             ret2 = c.timings[13] > 0 ? c.timings[13] : 1.0;  // merge GEMM flops (mx_pdlaed1.F:291,304); > 0 keeps ret positive
             if (mode == 'X') { if (penta) bisect2_dev(n, d_d, e_d, e2_d, w_d); else bisect_dev(n, d_d, e_d, w_d); }
             T.mark(3);
+            copy_a_back();
             // ---- back-transformation (eigen_s.F:245-248) ------------------------------------
             // host arrays: Z goes to the caller chunk by chunk on the side stream, behind the GEMMs of the next chunk
             if (!dev_ptrs && nrl > 0 && nvl > 0) { trbak_set_host_output(z, ldz); z_streamed = true; }
@@ -284,7 +289,8 @@ static void eigen_s_body(int n, int nvec, double *a, int lda, double *w, double 
     } else { T.mark(2); T.mark(3); T.mark(4); }
     T.mark(5);
     EE_CUDA(cudaStreamSynchronize(st));
-    if (a_copied_back || z_streamed) EE_CUDA(cudaStreamSynchronize(c.stream2));
+    if (z_streamed) EE_CUDA(cudaStreamSynchronize(c.stream2));
+    if (a_copied_back) EE_CUDA(cudaStreamSynchronize(c.stream3));
     c.timings[0] = T.sec(0, 1); c.timings[1] = T.sec(1, 2); c.timings[2] = T.sec(2, 3);
     c.timings[3] = T.sec(3, 4); c.timings[4] = T.sec(4, 5);
     // ---- a(1:3,1) = flop count, seconds, comm seconds (-1: timers off) (eigen_s.F:284-295) ---
@@ -361,6 +367,7 @@ try {
     c.g = g;
     EE_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     EE_CUDA(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
+    EE_CUDA(cudaStreamCreateWithFlags(&c.stream3, cudaStreamNonBlocking));
     EE_CUDA(cudaEventCreateWithFlags(&c.ev_side, cudaEventDisableTiming));
     pool_create(c.device);
     if (comm_init(comm ? comm->unique_id : nullptr, rank, nranks, g) != 0) return;
@@ -377,8 +384,8 @@ try {
     c.ev_pool.clear();
     pool_destroy();
     if (c.ev_side) { cudaEventDestroy(c.ev_side); c.ev_side = nullptr; }
-    cudaStreamDestroy(c.stream); cudaStreamDestroy(c.stream2);
-    c.stream = c.stream2 = nullptr;
+    cudaStreamDestroy(c.stream); cudaStreamDestroy(c.stream2); cudaStreamDestroy(c.stream3);
+    c.stream = c.stream2 = c.stream3 = nullptr;
     c.initialized = false;
 } catch (const ::ee::FatalError &) { ::ee::ctx().errinfo = -1; }
 

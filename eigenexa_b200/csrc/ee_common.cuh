@@ -62,6 +62,7 @@ struct Context {
     int device = 0;
     cudaStream_t stream = nullptr;   // main stream: every kernel of the path
     cudaStream_t stream2 = nullptr;  // copies / side work
+    cudaStream_t stream3 = nullptr;  // reflectors back to the caller's a (its own stream: stream2 carries the V prefetch)
     cudaEvent_t ev_side = nullptr;   // main stream -> side stream hand-over
     Comm *comm = nullptr;
     int errinfo = 0;
