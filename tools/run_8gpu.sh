@@ -17,7 +17,7 @@ for w in $WHAT; do
       timeout 500 $TR bench.py --gpus 8 --steps 5 --warmup 3 --budget-s 230 > gpurun_out/r02_bench_n8.log 2> gpurun_out/r02_bench_n8.err
       tail -c 1500 gpurun_out/r02_bench_n8.log; tail -2 gpurun_out/r02_bench_n8.err ;;
     config5)
-      EIGENEXA_BENCH_N=100000 EIGENEXA_BENCH_SOLVER=sx timeout 600 $TR bench.py --gpus 8 --steps 1 --warmup 1 --budget-s 330 --no-e2e \
+      EIGENEXA_BENCH_N=100000 EIGENEXA_BENCH_SOLVER=sx timeout 600 $TR bench.py --gpus 8 --steps 1 --warmup 0 --cold --budget-s 330 --no-e2e \
         > gpurun_out/r02_bench_sx_n100000_8.log 2> gpurun_out/r02_bench_sx_n100000_8.err
       tail -c 1800 gpurun_out/r02_bench_sx_n100000_8.log; tail -3 gpurun_out/r02_bench_sx_n100000_8.err ;;
   esac
