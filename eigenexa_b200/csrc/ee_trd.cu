@@ -1596,6 +1596,32 @@ double scaling_dev(int n, double *a, int lda)
     return sigma;
 }
 
+// Launch shape of the multi-launch SYMV kernels (symv_kernel / symv2_kernel) for a trailing matrix of order L:
+// strip length sw (tiles) and the folded grid gx x gy (fold_triangle: CTA column bx sweeps strip nsc-1-bx, then strip bx;
+// gy = most tile rows any CTA column needs).  Long strips amortise the row-sum reduction at large L, short ones give the
+// latency-bound small trailing matrices more CTAs.  Returns sw.
+static int symv_launch_shape(const Grid &g, int L, int nclL, int *gx_out, int *gy_out)
+{
+    const int sw = (L > 12288) ? 4 : (L > 6144) ? 2 : 1;
+    const int nsc = (nclL + sw * TC - 1) / (sw * TC);
+    int gx = (nsc + 1) / 2, gy = 0;
+    auto strip_rows_h = [&](int sc) {       // host twin of strip_rows()
+        int tlast = std::min((sc + 1) * sw, (nclL + TC - 1) / TC) - 1;
+        int clast = std::min((tlast + 1) * TC, nclL) - 1;
+        if (clast < tlast * TC) return 0;
+        long long cmax_g = (long long)clast * g.py + g.y;
+        if (cmax_g <= g.x) return 0;
+        return (int)((cmax_g - g.x - 1) / ((long long)TR * g.px)) + 1;
+    };
+    for (int bx = 0; bx < gx; bx++) {
+        int s1 = nsc - 1 - bx, s2 = bx;
+        int r = strip_rows_h(s1) + (s2 != s1 ? strip_rows_h(s2) : 0);
+        if (r > gy) gy = r;
+    }
+    *gx_out = gx; *gy_out = gy;
+    return sw;
+}
+
 // local padded dims used by the trd kernels
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 int trd_lda_pad(int nrl) { return round_up(nrl > 0 ? nrl : 1, TR); }
@@ -1801,26 +1827,8 @@ void trd_dev(int n, double *a_user, int lda_user, double *d_out, double *e_out, 
             const int nclL = cyc_count(L, g.py, g.y);
             // long strips amortise the row-sum reduction at large L; short ones give the
             // latency-bound small trailing matrices more CTAs
-            const int sw = (L > 12288) ? 4 : (L > 6144) ? 2 : 1;
-            Q.sw = sw;
-            const int nsc = (nclL + sw * TC - 1) / (sw * TC);
-            int gx = (nsc + 1) / 2, gy = 0;
-            if (nsc > 0) {
-                // rows of the biggest strip + rows of the smallest
-                auto strip_rows_h = [&](int sc) {
-                    int tlast = std::min((sc + 1) * sw, (nclL + TC - 1) / TC) - 1;
-                    int clast = std::min((tlast + 1) * TC, nclL) - 1;
-                    if (clast < tlast * TC) return 0;
-                    long long cmax_g = (long long)clast * g.py + g.y;
-                    if (cmax_g <= g.x) return 0;
-                    return (int)((cmax_g - g.x - 1) / ((long long)TR * g.px)) + 1;
-                };
-                for (int bx = 0; bx < gx; bx++) {
-                    int s1 = nsc - 1 - bx, s2 = bx;
-                    int r = strip_rows_h(s1) + (s2 != s1 ? strip_rows_h(s2) : 0);
-                    if (r > gy) gy = r;
-                }
-            }
+            int gx, gy;
+            Q.sw = symv_launch_shape(g, L, nclL, &gx, &gy);
             const int ntile_blocks = gx * gy;
             const int nblocks = ntile_blocks + (Q.ndone > 0 ? NCH : 0);
             prof_begin(1);
@@ -2040,25 +2048,8 @@ void prd_dev(int n, double *a_user, int lda_user, double *d_out, double *e1_out,
             EE_CHECK_LAUNCH();
             // ---- [p_a p_b] = A [u_a u_b] in one pass --------------------------------------------------
             const int nclL = cyc_count(L, g.py, g.y);
-            const int sw = (L > 12288) ? 4 : (L > 6144) ? 2 : 1;
-            Q.sw = sw;
-            const int nsc = (nclL + sw * TC - 1) / (sw * TC);
-            int gx = (nsc + 1) / 2, gy = 0;
-            if (nsc > 0) {
-                auto strip_rows_h = [&](int sc) {
-                    int tlast = std::min((sc + 1) * sw, (nclL + TC - 1) / TC) - 1;
-                    int clast = std::min((tlast + 1) * TC, nclL) - 1;
-                    if (clast < tlast * TC) return 0;
-                    long long cmax_g = (long long)clast * g.py + g.y;
-                    if (cmax_g <= g.x) return 0;
-                    return (int)((cmax_g - g.x - 1) / ((long long)TR * g.px)) + 1;
-                };
-                for (int bx = 0; bx < gx; bx++) {
-                    int s1 = nsc - 1 - bx, s2 = bx;
-                    int r = strip_rows_h(s1) + (s2 != s1 ? strip_rows_h(s2) : 0);
-                    if (r > gy) gy = r;
-                }
-            }
+            int gx, gy;
+            Q.sw = symv_launch_shape(g, L, nclL, &gx, &gy);
             const int ntile_blocks = gx * gy;
             const int nblocks = ntile_blocks + (Q.ndone > 0 ? NCH : 0);
             mark(1);
