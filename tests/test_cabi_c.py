@@ -68,3 +68,11 @@ def test_c_translation_unit_solves_like_c_test(tmp_path):
     _compile("cabi_gpu.c", exe)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "CABI_GPU_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_mpi_shim_compiles_against_the_header():
+    """bindings/eigen_init_mpi.c (the MPI-side glue of INTEGRATION.md section 1) type-checks against
+    include/eigenexa_b200.h; MPI itself is stubbed (tests/c/mpi_stub/mpi.h): the image has no MPI."""
+    subprocess.check_call(["gcc", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(ROOT, "tests", "c", "mpi_stub"),
+                           os.path.join(ROOT, "bindings", "eigen_init_mpi.c")])
