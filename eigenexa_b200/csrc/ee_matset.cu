@@ -5,7 +5,8 @@
 // random_number with the rank id (mat_set.f:167-179), which is neither portable across
 // compilers nor across grids; here R(i,j) is a counter-based hash of (seed, i, j) so every
 // grid (and the CPU oracle) builds the same global matrix.
-// ev_test (benchmark/ev_test.f:113-205): |AZ-ZW|_F/(N eps |A|_F) and |Z^T Z-I|_F/(N eps).
+// ev_test (benchmark/ev_test.f:113-205): |AZ-ZW|_F/(N eps |A|_F) and |Z^T Z-I|_F/(N eps); on one rank from the
+// full matrix, on a grid distributed like the reference's (ev_test.f:81-164) -- see ev_test_dist.
 #include "ee_common.cuh"
 #include "ee_comm.h"
 #include <thread>

@@ -9,8 +9,10 @@
 // reference there is no separate unblocked "head" (trbakwy4.F:345-499): the leading
 // (n-1) mod mb reflectors simply form a first, shorter block.
 // All O(n^2 mb) work is FP64 tensor-core GEMM (ee_gemm.cu); on a P x Q grid the V panel is
-// assembled replicated (one all-reduce of disjoint pieces) and V^T Z is summed over the
-// x group, as in trbakwy4_body.F:235.
+// assembled replicated (pack of the owned pieces + one all-gather + unpack, prefetched one block
+// ahead on the side stream: trbakwy4.F:508-602 prefetches two ahead) and V^T Z is summed over the
+// x group, as in trbakwy4_body.F:235.  With a host destination, Z is processed in column chunks and
+// every finished chunk leaves for the host behind the GEMMs of the next one.
 #include "ee_common.cuh"
 #include "ee_comm.h"
 #include <chrono>

@@ -11,16 +11,19 @@
 //  * the local part of A stays in HBM in the caller's 2D cyclic layout; every vector of the
 //    algorithm (current column, panel copy W, reflector panels U and V, p = A u) is kept
 //    FULL LENGTH and replicated on every rank, so one column step needs exactly one
-//    cross-rank reduction (of the partial p) instead of the reference's
+//    cross-rank exchange (of the partial p) instead of the reference's
 //    redistribution + 2 all-reduces + broadcast (src/eigen_trd_t2.F:426-567).
-//  * one column step = three launches, no host synchronisation anywhere:
-//      symv_kernel   streams the local strict upper "staircase" once (HBM-bound): each
-//                    element feeds a column dot and a row axpy (K1 of SURVEY 2.4), writes
-//                    deterministic per-tile partials; a few extra CTAs compute U^T u, V^T u.
-//      pvec_kernel   p = sum(partials) + diag*u - U s - V t ; partial u^T p.
-//      vvec_kernel   v = (p - alpha u)/beta ; forms the next column from the panel copy
-//                    (left-looking) and its norm; the last CTA finishes the Householder
-//                    scalars (g, u_L, beta) on the device.
+//  * eigen_trd: ALL column steps of a panel run inside ONE persistent cooperative launch
+//    (trd_panel_kernel, further down): per column a SYMV phase over the local strict upper
+//    "staircase" (HBM-bound: each element feeds a column dot and a row axpy, K1 of SURVEY 2.4;
+//    deterministic per-tile partials; the panel dot products U^T u, V^T u ride along as work
+//    items), a p phase (sum of partials + diag*u - U s - V t, on a grid the exchange over NVLink
+//    peer memory, partial u^T p) and a v phase (v = (p - alpha u)/beta, next column from the panel
+//    copy, left-looking, and its norm), separated by grid barriers; the Householder scalars
+//    (g, u_L, beta, alpha) are reduced redundantly by every CTA and never leave the device.
+//  * the three-launch form of the same step (symv_kernel -> pvec_kernel -> vvec_kernel) is kept
+//    as the debugging reference / fallback (EIGENEXA_B200_TRD_PERSIST=0, or no peer ring on a grid),
+//    and eigen_prd still uses its four-launch form (next2 -> house2 -> symv2 -> pvec2).
 //  * the trailing update A -= U V^T + V U^T is one FP64 tensor-core (DMMA) GEMM with K = 2m
 //    on the upper staircase tiles (ee_gemm.cu).
 // All reductions have a fixed order: results are bit-reproducible run to run.
