@@ -179,9 +179,12 @@ void *eigenexa_b200_stream(void);   /* cudaStream_t of the library (for event ti
 /* ---- instrumentation ------------------------------------------------------------- */
 /* number of kernels this library launched since the last reset (bench gpu_launches)  */
 int64_t eigenexa_b200_launch_count(int reset);
-/* stage timings of the last eigen_s call on this rank, seconds (CUDA events):
- * t[0]=h2d t[1]=scaling+trd t[2]=tridiagonal solver t[3]=back-transform t[4]=d2h
- * t[5]=symv kernels total t[6]=syr2k kernels total (filled when profiling is on)      */
+/* stage timings of the last eigen_s call on this rank, seconds (CUDA events), up to 48 slots:
+ * t[0]=h2d t[1]=scaling+trd t[2]=tridiagonal solver t[3]=back-transform t[4]=d2h (w only: a and z stream out earlier)
+ * with profiling on:  t[5]=panel kernels of eigen_trd (or symv launches on the multi-launch paths)  t[6]=rank-2k GEMMs
+ * t[13]=merge GEMM flops of the D&C  t[17..21]=D&C breakdown
+ * persistent panel kernel, in-kernel %globaltimer of CTA 0:  t[15]=SYMV phase  t[16]=p phase  t[31]=v phase;
+ * on a grid, inside the p phase:  t[32]=partial sums  t[33]=grid barrier  t[34]=corrections + flag round  t[35]=peer sum */
 void eigenexa_b200_last_timings(double *t, int nt);
 void eigenexa_b200_set_profiling(int level); /* 0 off, 1 async events (symv, syr2k), 2 debug */
 /* per-launch symv_kernel milliseconds of the last eigen_trd (first entry = column n);
