@@ -24,7 +24,7 @@ cannot all run inside the harness limits.  After the first warm-up solve the ste
 the number of warm-up and timed solves is then clamped so that the whole run (resident leg, parity
 check, end-to-end leg, CPU leg) ends within --budget-s seconds of process start.  The JSON line
 reports the steps actually timed (`steps`, `warmup`) next to `requested_steps` / `requested_warmup`.
-A complete line is flushed right after the resident leg (`"partial": true`); the final line follows.
+A complete line is flushed to stderr right after the resident leg (`"partial": true`); the one stdout line follows at the end.
 """
 from __future__ import annotations
 
@@ -423,8 +423,13 @@ def main():
         return line
 
     if rank == 0:
-        # a complete line right after the resident leg: a kill during the later legs still leaves a record
-        print(json.dumps(make_line(None, None, None, True)), flush=True)
+        # a complete line right after the resident leg: a kill during the later legs still leaves a record.  It goes to
+        # STDERR (the harness keeps stderr_tail) so that stdout carries exactly ONE JSON line, the final one
+        # (EIGENEXA_BENCH_PARTIAL_STDOUT=1 puts it on stdout as well).
+        early = json.dumps(make_line(None, None, None, True))
+        print(early, file=sys.stderr, flush=True)
+        if os.environ.get("EIGENEXA_BENCH_PARTIAL_STDOUT") == "1":
+            print(early, flush=True)
 
     # parity of the timed result, size-independent property (benchmark/ev_test.f on the device, on the grid)
     check = None
